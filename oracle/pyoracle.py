@@ -1,0 +1,254 @@
+"""ctypes access to the oracle (TEST INFRASTRUCTURE ONLY -- see oracle/oracle.h).
+
+  * ``liboracle.so``          our plain-C restatement (oracle/fsk_oracle.c, dft_oracle.c)
+  * ``_ref/libfsk_ref.so``    the UNMODIFIED reference modem + our in-memory frame pump
+  * ``_ref/fsk_demod``, ``_ref/dft_detect``   the reference CLIs
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(HERE, "_ref")
+FMT = {"cs16": 0, "f32": 1, "cu8": 2, "s16": 3}
+
+
+def build(verbose: bool = False) -> None:
+    """Compile liboracle.so and (when /root/reference is present) oracle/_ref/."""
+    r = subprocess.run(["make", "-C", HERE, "all"], capture_output=True, text=True)
+    if verbose or r.returncode:
+        print(r.stdout, r.stderr)
+    if r.returncode:
+        raise RuntimeError("oracle build failed")
+
+
+def _load(path: str) -> C.CDLL:
+    if not os.path.exists(path):
+        build()
+    return C.CDLL(path)
+
+
+class FrameRec(C.Structure):
+    _fields_ = [("nin_used", C.c_int), ("nin_next", C.c_int), ("norm_rx_timing", C.c_float),
+                ("rx_timing", C.c_float), ("ppm", C.c_float), ("EbNodB", C.c_float), ("snr_est", C.c_float),
+                ("foff", C.c_float), ("f_est", C.c_float * 4), ("mean_sum", C.c_float), ("std_sum", C.c_float)]
+
+
+REC_DTYPE = np.dtype([("nin_used", "i4"), ("nin_next", "i4"), ("norm_rx_timing", "f4"), ("rx_timing", "f4"),
+                      ("ppm", "f4"), ("EbNodB", "f4"), ("snr_est", "f4"), ("foff", "f4"), ("f_est", "f4", (4,)),
+                      ("mean_sum", "f4"), ("std_sum", "f4")])
+assert REC_DTYPE.itemsize == C.sizeof(FrameRec)
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        L = _load(os.path.join(HERE, "liboracle.so"))
+        L.fsko_create.restype = C.c_void_p
+        L.fsko_create.argtypes = [C.c_int] * 7
+        L.fsko_destroy.argtypes = [C.c_void_p]
+        L.fsko_set_freq_est_limits.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.fsko_set_freq_est_alg.argtypes = [C.c_void_p, C.c_int]
+        L.fsko_nin.argtypes = [C.c_void_p]
+        L.fsko_nbits.argtypes = [C.c_void_p]
+        L.fsko_ndft.argtypes = [C.c_void_p]
+        L.fsko_param.argtypes = [C.c_void_p, C.c_char_p]
+        L.fsko_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        for f in ("fsko_Sf", "fsko_hann", "fsko_twiddles", "fsko_f_int", "fsko_f_dc", "fsko_phi_c"):
+            getattr(L, f).restype = C.POINTER(C.c_float)
+            getattr(L, f).argtypes = [C.c_void_p]
+        L.fsko_last_frame.argtypes = [C.c_void_p, C.POINTER(FrameRec)]
+        L.fsko_fft.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.fsko_eye.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+        L.fsko_run_stream.restype = C.c_long
+        L.fsko_run_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int,
+                                      C.c_void_p, C.POINTER(C.c_long), C.c_void_p, C.c_long]
+        _lib = L
+    return _lib
+
+
+@dataclass
+class FskConfig:
+    """fsk_demod command-line parameters (utils/fsk_demod.c:53-232)."""
+    Fs: int = 48000
+    Rs: int = 4800
+    M: int = 2
+    P: int = 10                 # CLI default (fsk_demod.c:71)
+    Nsym: int = 50              # FSK_DEFAULT_NSYM (fsk.h:46)
+    lower: int | None = None    # --fsk_lower; None -> -Fs/2 for complex input (fsk_demod.c:218-226)
+    upper: int | None = None
+    mask: int = 0               # --mask TxSpacing: 0 = peak estimator
+    soft: bool = True
+    softinv: bool = False
+
+    @property
+    def fs_tx(self) -> int:
+        return self.mask if self.mask else 100           # fsk_demod.c:79,159
+
+    @property
+    def lo(self) -> int:
+        return -self.Fs // 2 if self.lower is None else self.lower
+
+    @property
+    def hi(self) -> int:
+        return self.Fs // 2 if self.upper is None else self.upper
+
+    def cli_args(self, fmt: str = "cs16") -> list[str]:
+        a = {"cs16": ["--cs16"], "cu8": ["--cu8"], "s16": []}[fmt]
+        if self.lower is not None:
+            a += ["-b", str(self.lower)]
+        if self.upper is not None:
+            a += ["-u", str(self.upper)]
+        if self.soft:
+            a += ["-s"]
+        if self.softinv:
+            a += ["-i"]
+        if self.mask:
+            a += ["--mask", str(self.mask)]
+        a += [f"--nsym={self.Nsym}", "-p", str(self.P), str(self.M), str(self.Fs), str(self.Rs)]
+        return a
+
+
+RS41 = FskConfig(48000, 4800, 2, 5, 300, -5000, 5000, 5000)          # auto_rx/autorx/decode.py:901
+
+
+class Oracle:
+    """One channel of the C restatement."""
+
+    def __init__(self, cfg: FskConfig):
+        self.cfg = cfg
+        self.L = lib()
+        self.h = self.L.fsko_create(cfg.Fs, cfg.Rs, cfg.M, cfg.P, cfg.Nsym, 1000, cfg.fs_tx)
+        self.L.fsko_set_freq_est_limits(self.h, cfg.lo, cfg.hi)
+        self.L.fsko_set_freq_est_alg(self.h, 1 if cfg.mask else 0)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.fsko_destroy(self.h)
+            self.h = None
+
+    def param(self, k: str) -> int:
+        return self.L.fsko_param(self.h, k.encode())
+
+    @property
+    def nin(self) -> int:
+        return self.L.fsko_nin(self.h)
+
+    def _arr(self, fn: str, n: int) -> np.ndarray:
+        return np.ctypeslib.as_array(getattr(self.L, fn)(self.h), shape=(n,)).copy()
+
+    def Sf(self):
+        return self._arr("fsko_Sf", self.param("Ndft"))
+
+    def hann(self):
+        return self._arr("fsko_hann", self.param("Ndft"))
+
+    def twiddles(self):
+        return self._arr("fsko_twiddles", 2 * self.param("Ndft"))
+
+    def f_int(self):
+        return self._arr("fsko_f_int", 2 * self.param("M") * (self.param("Nsym") + 1) * self.param("P"))
+
+    def f_dc(self):
+        return self._arr("fsko_f_dc", 2 * self.param("M") * self.param("Nmem"))
+
+    def phi_c(self):
+        return self._arr("fsko_phi_c", 2 * self.param("M"))
+
+    def fft(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        y = np.empty_like(x)
+        self.L.fsko_fft(self.h, x.ctypes.data, y.ctypes.data)
+        return y
+
+    def frame(self, iq: np.ndarray, soft: bool = True):
+        iq = np.ascontiguousarray(iq, dtype=np.float32)
+        nb = self.L.fsko_nbits(self.h)
+        if soft:
+            o = np.zeros(nb, np.float32)
+            self.L.fsko_frame(self.h, iq.ctypes.data, None, o.ctypes.data)
+        else:
+            o = np.zeros(nb, np.uint8)
+            self.L.fsko_frame(self.h, iq.ctypes.data, o.ctypes.data, None)
+        return o
+
+    def last(self) -> FrameRec:
+        r = FrameRec()
+        self.L.fsko_last_frame(self.h, C.byref(r))
+        return r
+
+    def run_stream(self, data: np.ndarray, fmt: str = "cs16"):
+        """CLI frame pump over memory -> (out, consumed, records)."""
+        data = np.ascontiguousarray(data)
+        per = {"cs16": 2, "f32": 2, "cu8": 2, "s16": 1}[fmt]
+        nsamp = data.size // per
+        nb = self.L.fsko_nbits(self.h)
+        maxf = nsamp // max(1, self.param("N") - self.param("Ts") // 2) + 2
+        out = np.zeros(maxf * nb, np.float32 if self.cfg.soft else np.uint8)
+        recs = np.zeros(maxf, REC_DTYPE)
+        cons = C.c_long(0)
+        nf = self.L.fsko_run_stream(self.h, data.ctypes.data, nsamp, FMT[fmt], int(self.cfg.soft),
+                                    int(self.cfg.softinv), out.ctypes.data, C.byref(cons), recs.ctypes.data, maxf)
+        return out[:nf * nb], cons.value, recs[:nf]
+
+
+# ------------------------------------------------------------------------------------------------
+# the UNMODIFIED reference (oracle/_ref)
+# ------------------------------------------------------------------------------------------------
+_ref = None
+REF_REC = 10
+
+
+def ref_available() -> bool:
+    return os.path.exists(os.path.join(REF_DIR, "libfsk_ref.so")) or os.path.isdir("/root/reference/utils")
+
+
+def reflib() -> C.CDLL:
+    global _ref
+    if _ref is None:
+        L = _load(os.path.join(REF_DIR, "libfsk_ref.so"))
+        L.ref_fsk_run_stream.restype = C.c_long
+        L.ref_fsk_run_stream.argtypes = [C.c_int] * 9 + [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int,
+                                                         C.c_void_p, C.POINTER(C.c_long), C.c_void_p, C.c_long, C.c_void_p]
+        _ref = L
+    return _ref
+
+
+def ref_run_stream(cfg: FskConfig, data: np.ndarray, fmt: str = "cs16", want_out: bool = True):
+    """Reference modem over an in-memory stream -> (out, consumed, recs[nf,10], Sf)."""
+    L = reflib()
+    data = np.ascontiguousarray(data)
+    per = {"cs16": 2, "f32": 2, "cu8": 2, "s16": 1}[fmt]
+    nsamp = data.size // per
+    Ts = cfg.Fs // cfg.Rs
+    N = Ts * cfg.Nsym
+    nb = cfg.Nsym * (1 if cfg.M == 2 else 2)
+    maxf = nsamp // max(1, N - Ts // 2) + 2
+    out = np.zeros(maxf * nb, np.float32 if cfg.soft else np.uint8) if want_out else None
+    recs = np.zeros((maxf, REF_REC), np.float32)
+    Sf = np.zeros(4096, np.float32)
+    cons = C.c_long(0)
+    nf = L.ref_fsk_run_stream(cfg.Fs, cfg.Rs, cfg.M, cfg.P, cfg.Nsym, cfg.fs_tx, cfg.lo, cfg.hi, 1 if cfg.mask else 0,
+                              data.ctypes.data, nsamp, FMT[fmt], int(cfg.soft), int(cfg.softinv),
+                              out.ctypes.data if want_out else None, C.byref(cons), recs.ctypes.data, maxf,
+                              Sf.ctypes.data)
+    return (out[:nf * nb] if want_out else None), cons.value, recs[:nf], Sf
+
+
+def ref_cli_fsk_demod(cfg: FskConfig, raw: bytes, fmt: str = "cs16", extra: list[str] | None = None):
+    """Run the reference fsk_demod binary on stdin bytes -> (stdout bytes, stderr bytes, rc)."""
+    exe = os.path.join(REF_DIR, "fsk_demod")
+    if not os.path.exists(exe):
+        build()
+    args = [exe] + (extra or []) + cfg.cli_args(fmt) + ["-", "-"]
+    r = subprocess.run(args, input=raw, capture_output=True)
+    return r.stdout, r.stderr, r.returncode

@@ -1,0 +1,91 @@
+"""Seeded synthetic IQ generators for the IQ->bits hot path (tests + bench).
+
+The reference ships no recorded IQ (fixtures are external downloads), so every
+workload is synthesised here, deterministically from ``numpy.random.default_rng(seed)``, and
+QUANTISED TO cs16 -- the byte format the reference CLIs read on stdin (utils/fsk_demod.c:281-309,
+scan/dft_detect.c:556-591) -- so the oracle and the CUDA path see bit-identical input.
+
+Nothing here is on the product path; it only manufactures input.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# 64-bit RS41 frame header as the reference detector spells it (scan/dft_detect.c:46-47).
+RS41_HEADER = "0000100001101101010100111000100001000100011010010100100000011111"
+
+
+def _bits_with_header(rng: np.random.Generator, nbits: int, header: str | None, period: int) -> np.ndarray:
+    bits = rng.integers(0, 2, size=nbits, dtype=np.uint8)
+    if header:
+        h = np.frombuffer(header.encode(), dtype=np.uint8) - ord("0")
+        for s in range(int(rng.integers(0, period)), nbits - len(h), period):
+            bits[s:s + len(h)] = h
+    return bits
+
+
+def fsk_iq(seed: int, nsamp: int, Fs: int = 48000, Rs: int = 4800, M: int = 2,
+           f_lo: float | None = None, spacing: float | None = None, ebno_db: float = 15.0,
+           ppm: float = 0.0, amp: float = 8000.0, header: str | None = RS41_HEADER,
+           header_period: int = 4800, return_bits: bool = False):
+    """Continuous-phase M-FSK at complex baseband -> cs16 array of shape (nsamp, 2), dtype int16.
+
+    Tone m sits at ``f_lo + m*spacing`` Hz.  ``ppm`` stretches the symbol clock, ``ebno_db`` sets
+    AWGN (complex, total variance N0 per sample; Es = amp^2 * Ts).  All randomness comes from ``seed``.
+    """
+    rng = np.random.default_rng(seed)
+    if spacing is None:
+        spacing = float(Rs)
+    if f_lo is None:
+        f_lo = -spacing * (M - 1) / 2.0 + float(rng.uniform(-2000.0, 2000.0))
+    bps = 1 if M == 2 else 2
+    Ts = Fs / Rs
+    nsym = int(nsamp / Ts * (1 + abs(ppm) * 1e-6)) + 4
+    bits = _bits_with_header(rng, nsym * bps, header, header_period)
+    if M == 2:
+        sym = bits.astype(np.int64)
+    else:
+        sym = (bits[0::2].astype(np.int64) << 1) | bits[1::2]
+    tau0 = float(rng.uniform(0.0, 1.0))
+    n = np.arange(nsamp, dtype=np.float64)
+    sidx = np.floor(n / Ts * (1.0 + ppm * 1e-6) + tau0).astype(np.int64)
+    f = f_lo + spacing * sym[sidx]
+    phase = 2.0 * np.pi * np.cumsum(f) / Fs + float(rng.uniform(0, 2 * np.pi))
+    sig = amp * np.exp(1j * phase)
+    ebno = 10.0 ** (ebno_db / 10.0)
+    n0 = amp * amp * Ts / (ebno * bps)
+    sigma = np.sqrt(n0 / 2.0)
+    noise = rng.standard_normal((nsamp, 2), dtype=np.float32).astype(np.float64) * sigma
+    out = np.empty((nsamp, 2), dtype=np.float64)
+    out[:, 0] = sig.real + noise[:, 0]
+    out[:, 1] = sig.imag + noise[:, 1]
+    iq = np.clip(np.rint(out), -32768, 32767).astype(np.int16)
+    if return_bits:
+        return iq, bits
+    return iq
+
+
+def noise_iq(seed: int, nsamp: int, sigma: float = 3000.0) -> np.ndarray:
+    """Noise-only channel (cs16)."""
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((nsamp, 2), dtype=np.float32) * sigma
+    return np.clip(np.rint(x), -32768, 32767).astype(np.int16)
+
+
+def fsk_batch(base_seed: int, nchan: int, nsamp: int, workers: int = 8, **kw) -> np.ndarray:
+    """``nchan`` independent channels -> int16 [nchan, nsamp, 2]; channel c uses seed base_seed+c,
+    a per-channel clock offset in +-50 ppm and Eb/N0 cycling over {10, 14, 20, 40} dB unless given."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    out = np.empty((nchan, nsamp, 2), dtype=np.int16)
+
+    def one(c: int) -> None:
+        k = dict(kw)
+        r = np.random.default_rng(base_seed * 7919 + c)
+        k.setdefault("ppm", float(r.uniform(-50.0, 50.0)))
+        k.setdefault("ebno_db", (10.0, 14.0, 20.0, 40.0)[c % 4])
+        out[c] = fsk_iq(base_seed + c, nsamp, **k)
+
+    with ThreadPoolExecutor(max_workers=workers) as ex:
+        list(ex.map(one, range(nchan)))
+    return out
