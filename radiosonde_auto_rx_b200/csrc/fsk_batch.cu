@@ -490,6 +490,18 @@ extern "C" int b200fsk_get_Sf(b200fsk_t *h, int c, float *Sf_out)
     return B200FSK_OK;
 }
 
+#ifdef FSK_PROFILE
+/* profiling build only: attach a zeroed [nchan][16] cycle-counter array and read it back */
+extern "C" int b200fsk_prof_read(b200fsk_t *h, long long *out)
+{
+    if (!h->kp.prof) { long long *d = 0; CK(zalloc(&d, (size_t)h->nchan * 16)); h->kp.prof = d; return 0; }
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out, h->kp.prof, sizeof(long long) * h->nchan * 16, cudaMemcpyDeviceToHost));
+    CK(cudaMemset(h->kp.prof, 0, sizeof(long long) * h->nchan * 16));
+    return 0;
+}
+#endif
+
 extern "C" long b200fsk_launch_count(const b200fsk_t *h) { return h ? h->launches : 0; }
 
 extern "C" float b200fsk_last_kernel_ms(b200fsk_t *h)

@@ -27,6 +27,16 @@
 #define FSK_WARPS   (FSK_THREADS / 32)
 #define FSK_MAXSTAGE 8
 
+#ifdef FSK_PROFILE   /* phase timing for profiles/: thread 0 accumulates clock64() deltas per phase */
+#define PROF_DECL long long prof_t = clock64(), prof_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define PROF(k) do { if (threadIdx.x == 0) { const long long t_ = clock64(); prof_acc[k] += t_ - prof_t; prof_t = t_; } } while (0)
+#define PROF_FLUSH do { if (threadIdx.x == 0 && p.prof) for (int k_ = 0; k_ < 12; ++k_) p.prof[blockIdx.x * 16 + k_] += prof_acc[k_]; } while (0)
+#else
+#define PROF_DECL
+#define PROF(k)
+#define PROF_FLUSH
+#endif
+
 struct FskFrameRec {            /* per-frame side record (host turns the sums into EbNodB with libm) */
     int   nin_used, nin_next;
     float norm_rx_timing, ppm;
@@ -56,6 +66,7 @@ struct FskKParams {
     void *out; long long out_stride; int soft, softinv; int *frame_base;
     FskFrameRec *recs; long long rec_stride; int write_recs;
     int *nframes; long long *consumed; float *eye_raw;
+    long long *prof;            /* FSK_PROFILE builds only: per-phase cycle counters [nchan][16] */
 };
 
 __device__ __forceinline__ float2 cmul_rn(float2 a, float2 b)       /* comp_prim.h:57-65 */
@@ -164,6 +175,7 @@ __global__ void __launch_bounds__(FSK_THREADS) fsk_demod_kernel(const FskKParams
     int frames = 0;
     unsigned char *outb = (unsigned char *)p.out + (long long)c * p.out_stride * (p.soft ? 4 : 1);
 
+    PROF_DECL
     while (true) {
         const int nin = s_nin;
         if ((p.max_frames > 0 && frames >= p.max_frames) || cursor + nin > p.nsamp) break;
@@ -172,6 +184,7 @@ __global__ void __launch_bounds__(FSK_THREADS) fsk_demod_kernel(const FskKParams
         /* ---- load + convert the frame (coalesced) ---- */
         for (int i = tid; i < nin; i += FSK_THREADS) x[i] = load_sample(p.in, p.fmt, base + cursor + i);
         __syncthreads();
+        PROF(0);
 
         /* ---- A: overlapping windowed FFTs -> Sf (fsk.c:465-503) ---- */
         const int numffts = (int)floorf(__fdiv_rn((float)nin, (float)(Ndft / 2))) - 1;
@@ -202,6 +215,7 @@ __global__ void __launch_bounds__(FSK_THREADS) fsk_demod_kernel(const FskKParams
             __syncthreads();
         }
 
+        PROF(1);
         /* ---- B + C(serial part): estimator, integrator memory shift, oscillators: warp 0 ---- */
         if (warp == 0) {
             int tabidx[4] = {0, 0, 0, 0};
@@ -241,6 +255,7 @@ __global__ void __launch_bounds__(FSK_THREADS) fsk_demod_kernel(const FskKParams
                 }
                 for (int m = 0; m < M; ++m) tabidx[m] = bm * M + m;
             }
+            PROF(2);
             /* integrator memory shift (fsk.c:637-640): source and destination never overlap (Nsym >= 4) */
             for (int e = lane; e < M * nold; e += 32) {
                 const int m = e / nold, i = e - m * nold;
@@ -260,6 +275,7 @@ __global__ void __launch_bounds__(FSK_THREADS) fsk_demod_kernel(const FskKParams
             }
         }
         __syncthreads();
+        PROF(3);
 
         /* ---- C(parallel part): down-convert, f_dc = x * conj(phi)  (fsk.c:648) ---- */
         for (int i = tid; i < nin; i += FSK_THREADS) {
@@ -270,6 +286,7 @@ __global__ void __launch_bounds__(FSK_THREADS) fsk_demod_kernel(const FskKParams
             }
         }
         __syncthreads();
+        PROF(4);
 
         /* ---- D: integrate and dump (fsk.c:659-668) ---- */
         for (int e = tid; e < M * nfi; e += FSK_THREADS) {
@@ -280,6 +297,7 @@ __global__ void __launch_bounds__(FSK_THREADS) fsk_demod_kernel(const FskKParams
             fint[e] = acc;
         }
         __syncthreads();
+        PROF(5);
 
         /* ---- E: fine timing (fsk.c:682-731) ---- */
         for (int i = tid; i < nfi; i += FSK_THREADS) {
@@ -289,6 +307,7 @@ __global__ void __launch_bounds__(FSK_THREADS) fsk_demod_kernel(const FskKParams
             x[i] = make_float2(__fmul_rn(ft1, ph.x), __fmul_rn(ft1, ph.y));
         }
         __syncthreads();
+        PROF(6);
         if (warp == 0 && lane < 2) {                                    /* sequential accumulate: re / im lanes */
             const float *t = (const float *)x + lane;
             float acc = 0.0f;
@@ -297,6 +316,7 @@ __global__ void __launch_bounds__(FSK_THREADS) fsk_demod_kernel(const FskKParams
             s_tc[lane] = acc;
         }
         __syncthreads();
+        PROF(7);
         if (tid == 0) {
             const float tr = s_tc[0], ti = s_tc[1];
             int nan = 0, nin_next = nin, high = s_high;
@@ -320,6 +340,7 @@ __global__ void __launch_bounds__(FSK_THREADS) fsk_demod_kernel(const FskKParams
             s_nan = nan; s_nin = nin_next;
         }
         __syncthreads();
+        PROF(8);
 
         /* ---- F: re-sample, decide, write (fsk.c:751-817) ---- */
         const long long ofs = (long long)(fbase + frames) * p.Nbits;
@@ -366,6 +387,7 @@ __global__ void __launch_bounds__(FSK_THREADS) fsk_demod_kernel(const FskKParams
             }
         }
         __syncthreads();
+        PROF(9);
 
         /* ---- EbNo sums (fsk.c:808-815) + frame record: warp 1 lanes 0/1, sequential ---- */
         if (warp == 1) {
@@ -386,7 +408,9 @@ __global__ void __launch_bounds__(FSK_THREADS) fsk_demod_kernel(const FskKParams
         }
         cursor += nin; ++frames;
         __syncthreads();
+        PROF(10);
     }
+    PROF_FLUSH;
 
     /* ---- launch epilogue: state back to HBM ---- */
     for (int i = tid; i < Ndft; i += FSK_THREADS) p.Sf[(long long)c * Ndft + i] = s_Sf[i];

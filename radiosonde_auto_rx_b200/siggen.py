@@ -47,19 +47,23 @@ def fsk_iq(seed: int, nsamp: int, Fs: int = 48000, Rs: int = 4800, M: int = 2,
     else:
         sym = (bits[0::2].astype(np.int64) << 1) | bits[1::2]
     tau0 = float(rng.uniform(0.0, 1.0))
-    n = np.arange(nsamp, dtype=np.float64)
-    sidx = np.floor(n / Ts * (1.0 + ppm * 1e-6) + tau0).astype(np.int64)
-    f = f_lo + spacing * sym[sidx]
-    phase = 2.0 * np.pi * np.cumsum(f) / Fs + float(rng.uniform(0, 2 * np.pi))
-    sig = amp * np.exp(1j * phase)
+    sidx = (np.arange(nsamp, dtype=np.float64) * ((1.0 + ppm * 1e-6) / Ts) + tau0).astype(np.int64)
+    f = (f_lo + spacing * sym)[sidx]
+    phase = np.cumsum(f)
+    phase *= 2.0 * np.pi / Fs
+    phase += float(rng.uniform(0, 2 * np.pi))
+    np.remainder(phase, 2.0 * np.pi, out=phase)
+    ph32 = phase.astype(np.float32)
     ebno = 10.0 ** (ebno_db / 10.0)
     n0 = amp * amp * Ts / (ebno * bps)
-    sigma = np.sqrt(n0 / 2.0)
-    noise = rng.standard_normal((nsamp, 2), dtype=np.float32).astype(np.float64) * sigma
-    out = np.empty((nsamp, 2), dtype=np.float64)
-    out[:, 0] = sig.real + noise[:, 0]
-    out[:, 1] = sig.imag + noise[:, 1]
-    iq = np.clip(np.rint(out), -32768, 32767).astype(np.int16)
+    sigma = np.float32(np.sqrt(n0 / 2.0))
+    out = rng.standard_normal((nsamp, 2), dtype=np.float32)
+    out *= sigma
+    out[:, 0] += np.float32(amp) * np.cos(ph32)
+    out[:, 1] += np.float32(amp) * np.sin(ph32)
+    np.rint(out, out=out)
+    np.clip(out, -32768, 32767, out=out)
+    iq = out.astype(np.int16)
     if return_bits:
         return iq, bits
     return iq
