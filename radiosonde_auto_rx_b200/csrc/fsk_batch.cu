@@ -19,7 +19,7 @@
 #include <vector>
 #include <string>
 #include "../../include/b200fsk.h"
-#include "fsk_kernel.cuh"
+#include "fsk_pipe_kernel.cuh"
 
 static thread_local std::string g_err;
 static int fail(int code, const char *fmt, ...)
@@ -33,7 +33,9 @@ struct b200fsk {
     b200fsk_cfg_t cfg; int nchan, device;
     int Ts, N, Nmem, Ndft, Nbits, nfi, ncap, tailcap, xcap;
     FskKParams kp;                     /* template of kernel params (tables/state pointers filled) */
-    size_t smem;
+    size_t smem;                       /* serial kernel */
+    size_t smem_pipe = 0; bool use_pipe = false;   /* pipelined kernel */
+    unsigned short *d_invperm = 0;
     std::vector<float> h_fest;         /* LUT: tone estimate in Hz per table index */
     /* device tables */
     float *d_hann = 0; float2 *d_tw = 0; unsigned short *d_perm = 0; float2 *d_phi_ft = 0; float *d_mask = 0; float2 *d_dphi = 0;
@@ -193,11 +195,31 @@ extern "C" int b200fsk_create(b200fsk_t **out, const b200fsk_cfg_t *cfg, int nch
     kp.o_Sf = take(Ndft * 4); kp.o_hann = take(Ndft * 4); kp.o_tw = take(Ndft * 8); kp.o_perm = take(Ndft * 2);
     kp.o_scr = take(Ndft * 4); kp.o_mask = take(Ndft * 4); kp.o_smax = take((size_t)Nsym * 8);
     h->smem = o;
+    /* pipelined kernel: usable when numffts does not depend on which of the three nin values a frame has */
+    {
+        const int nmin = N - Ts / 2, nmax = N + Ts / 2;
+        const int f0 = (int)floor((float)nmin / (Ndft / 2)), f1 = (int)floor((float)nmax / (Ndft / 2));
+        size_t q = 0;
+        auto takeq = [&](size_t bytes) { size_t r = q; q += (bytes + 15) & ~(size_t)15; return (int)r; };
+        kp.q_ring = takeq((size_t)M * PIPE_R * 8); kp.q_fint = takeq((size_t)M * nfi * 8); kp.q_stage_bytes = M * nfi * 8;
+        kp.q_fft = takeq((size_t)PIPE_NEST * Ndft * 8); kp.q_mag = takeq((size_t)PIPE_NEST * Ndft * 4);
+        kp.q_Sf = takeq((size_t)2 * Ndft * 4); kp.q_hann = takeq(Ndft * 4); kp.q_tw = takeq(Ndft * 8); kp.q_perm = takeq(Ndft * 2);
+        kp.q_scr = takeq(Ndft * 4); kp.q_mask = takeq(Ndft * 4); kp.q_smax = takeq((size_t)Nsym * 8); kp.q_tbuf = takeq(32 * 8);
+        h->smem_pipe = q;
+        const char *force = getenv("B200FSK_KERNEL");
+        h->use_pipe = (f0 == f1) && (f0 - 1 >= 1) && (3 * Ts + 2 * PIPE_BLK + 16 <= PIPE_R) && (Ts % 2 == 0 || true) &&
+                      (h->smem_pipe + 1024 <= (size_t)227 * 1024);
+        if (force && !strcmp(force, "serial")) h->use_pipe = false;
+    }
     int maxsmem = 0;
     CK(cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     if (h->smem + 256 > (size_t)maxsmem) { delete h; return fail(B200FSK_ENOMEM, "frame working set %zu B exceeds shared memory %d B", h->smem, maxsmem); }
     CK(cudaFuncSetAttribute(fsk_demod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    if (h->use_pipe) CK(cudaFuncSetAttribute(fsk_demod_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_pipe));
 
+    std::vector<unsigned short> invperm(Ndft);
+    for (int pos = 0; pos < Ndft; ++pos) invperm[perm[pos]] = (unsigned short)pos;
+    CK(upload(&h->d_invperm, invperm));
     CK(upload(&h->d_hann, hann)); CK(upload(&h->d_tw, tw)); CK(upload(&h->d_perm, perm));
     CK(upload(&h->d_phi_ft, phi_ft)); CK(upload(&h->d_mask, mask)); CK(upload(&h->d_dphi, dphi));
     CK(zalloc(&h->d_Sf, (size_t)nchan * Ndft)); CK(zalloc(&h->d_tail, (size_t)nchan * M * h->tailcap));
@@ -209,7 +231,7 @@ extern "C" int b200fsk_create(b200fsk_t **out, const b200fsk_cfg_t *cfg, int nch
         std::vector<int> nin(nchan, N);
         CK(upload(&h->d_phi, phi)); CK(upload(&h->d_nin, nin));
     }
-    kp.hann = h->d_hann; kp.tw = h->d_tw; kp.perm = h->d_perm; kp.phi_ft = h->d_phi_ft; kp.mask = h->d_mask; kp.dphi_tab = h->d_dphi;
+    kp.hann = h->d_hann; kp.tw = h->d_tw; kp.perm = h->d_perm; kp.phi_ft = h->d_phi_ft; kp.mask = h->d_mask; kp.dphi_tab = h->d_dphi; kp.invperm = h->d_invperm;
     kp.Sf = h->d_Sf; kp.phi_c = h->d_phi; kp.fdc_tail = h->d_tail; kp.nrt = h->d_nrt; kp.ppm = h->d_ppm; kp.nin = h->d_nin;
     kp.last_out = h->d_last; kp.tot_frames = h->d_totf; kp.tot_samples = h->d_tots;
     kp.nframes = h->d_nframes; kp.consumed = h->d_consumed; kp.eye_raw = h->d_eye;
@@ -226,7 +248,7 @@ extern "C" void b200fsk_destroy(b200fsk_t *h)
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    void *ptrs[] = {h->d_hann, h->d_tw, h->d_perm, h->d_phi_ft, h->d_mask, h->d_dphi, h->d_Sf, h->d_phi, h->d_tail, h->d_nrt,
+    void *ptrs[] = {h->d_invperm, h->d_hann, h->d_tw, h->d_perm, h->d_phi_ft, h->d_mask, h->d_dphi, h->d_Sf, h->d_phi, h->d_tail, h->d_nrt,
                     h->d_ppm, h->d_nin, h->d_last, h->d_totf, h->d_tots, h->d_nframes, h->d_consumed, h->d_eye, h->d_recs,
                     h->d_stage, h->d_off, h->d_out};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -238,7 +260,7 @@ extern "C" int b200fsk_info(const b200fsk_t *h, b200fsk_info_t *info)
 {
     if (!h || !info) return fail(B200FSK_EINVAL, "null");
     info->Ts = h->Ts; info->N = h->N; info->Nmem = h->Nmem; info->Ndft = h->Ndft; info->Nbits = h->Nbits;
-    info->nin_max = h->N + h->Ts / 2; info->nin_min = h->N - h->Ts / 2; info->nchan = h->nchan; info->smem_bytes = h->smem;
+    info->nin_max = h->N + h->Ts / 2; info->nin_min = h->N - h->Ts / 2; info->nchan = h->nchan; info->smem_bytes = h->use_pipe ? h->smem_pipe : h->smem;
     return B200FSK_OK;
 }
 
@@ -303,7 +325,8 @@ static int flush_pending(b200fsk *h)
 static int launch(b200fsk *h, FskKParams &kp, cudaStream_t s, bool time_it)
 {
     if (time_it) CK(cudaEventRecord(h->ev0, s));
-    fsk_demod_kernel<<<h->nchan, FSK_THREADS, h->smem, s>>>(kp);
+    if (h->use_pipe) fsk_demod_pipe_kernel<<<h->nchan, FSK_THREADS, h->smem_pipe, s>>>(kp);
+    else fsk_demod_kernel<<<h->nchan, FSK_THREADS, h->smem, s>>>(kp);
     CK(cudaGetLastError());
     if (time_it) { CK(cudaEventRecord(h->ev1, s)); h->timed = true; }
     h->launches++;

@@ -54,9 +54,11 @@ struct FskKParams {
     int neyesamp, eye_dec, eye_traces;
     /* shared-memory byte offsets */
     int o_x, o_fdc, o_fint, o_fft, o_mag, o_Sf, o_hann, o_tw, o_perm, o_scr, o_mask, o_smax;
+    /* shared-memory byte offsets of the pipelined kernel (fsk_pipe_kernel.cuh) */
+    int q_ring, q_fint, q_fft, q_mag, q_Sf, q_hann, q_tw, q_perm, q_scr, q_mask, q_smax, q_tbuf, q_stage_bytes;
     /* tables (global, read-only) */
     const float *hann; const float2 *tw; const unsigned short *perm; const float2 *phi_ft;
-    const float *mask; const float2 *dphi_tab;
+    const float *mask; const float2 *dphi_tab; const unsigned short *invperm;
     /* persistent per-channel state (global) */
     float *Sf; float2 *phi_c; float2 *fdc_tail; float *nrt; float *ppm; int *nin;
     unsigned int *last_out; long long *tot_frames; long long *tot_samples;
@@ -127,6 +129,53 @@ __device__ __forceinline__ void warp_fft(float2 *F, const float2 *tw, const FskK
             }
         }
         __syncwarp();
+    }
+}
+
+/* Tone estimate of one frame by ONE warp, from the final Sf of that frame: the peak picker (fsk.c:507-547) or
+ * the mask correlator (fsk.c:566-581), whichever fsk_set_freq_est_alg selected.  Returns, for each tone, the
+ * index into the host-built (cos,sin) oscillator-step LUT.  Ties resolve to the lowest bin, as the
+ * reference's strict `>` scan does. */
+__device__ __forceinline__ void estimate_tones(const FskKParams &p, const float *s_Sf, float *scr, const float *s_mask,
+                                               int lane, int tabidx[4])
+{
+    const int M = p.M, Ndft = p.Ndft;
+    tabidx[0] = tabidx[1] = tabidx[2] = tabidx[3] = 0;
+    if (p.est_type == 0) {
+        for (int i = lane; i < Ndft; i += 32) scr[i] = s_Sf[i];
+        __syncwarp();
+        int freqi[4] = {0, 0, 0, 0};
+        for (int k = 0; k < M; ++k) {
+            float mx = 0.0f; int im = 0;
+            for (int j = p.st + lane; j < p.en; j += 32) { const float v = scr[j]; if (v > mx) { mx = v; im = j; } }
+            for (int off = 16; off; off >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, mx, off);
+                const int   oi = __shfl_xor_sync(0xffffffffu, im, off);
+                if (ov > mx || (ov == mx && oi < im)) { mx = ov; im = oi; }
+            }
+            const int f_min = max(im - p.f_zero, 0), f_max = min(im + p.f_zero, Ndft);
+            for (int j = f_min + lane; j < f_max; j += 32) scr[j] = 0.0f;
+            __syncwarp();
+            freqi[k] = im - Ndft / 2;
+        }
+        for (int i = 1; i < M;) {                               /* gnome sort, fsk.c:533-542 */
+            if (freqi[i] >= freqi[i - 1]) ++i;
+            else { const int t = freqi[i]; freqi[i] = freqi[i - 1]; freqi[i - 1] = t; if (i > 1) --i; }
+        }
+        for (int m = 0; m < M; ++m) tabidx[m] = freqi[m] + Ndft / 2;
+    } else {
+        float cm = 0.0f; int bm = p.st;
+        for (int b = p.st + lane; b < p.en - p.len_mask; b += 32) {
+            float corr = 0.0f;
+            for (int i = 0; i < p.len_mask; ++i) corr = __fadd_rn(corr, __fmul_rn(s_mask[i], s_Sf[b + i]));
+            if (corr > cm) { cm = corr; bm = b; }
+        }
+        for (int off = 16; off; off >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, cm, off);
+            const int   ob = __shfl_xor_sync(0xffffffffu, bm, off);
+            if (ov > cm || (ov == cm && ob < bm)) { cm = ov; bm = ob; }
+        }
+        for (int m = 0; m < M; ++m) tabidx[m] = bm * M + m;
     }
 }
 
@@ -218,43 +267,8 @@ __global__ void __launch_bounds__(FSK_THREADS) fsk_demod_kernel(const FskKParams
         PROF(1);
         /* ---- B + C(serial part): estimator, integrator memory shift, oscillators: warp 0 ---- */
         if (warp == 0) {
-            int tabidx[4] = {0, 0, 0, 0};
-            if (p.est_type == 0) {                                      /* peak picker, fsk.c:507-547 */
-                for (int i = lane; i < Ndft; i += 32) scr[i] = s_Sf[i];
-                __syncwarp();
-                int freqi[4] = {0, 0, 0, 0};
-                for (int k = 0; k < M; ++k) {
-                    float mx = 0.0f; int im = 0;
-                    for (int j = p.st + lane; j < p.en; j += 32) { const float v = scr[j]; if (v > mx) { mx = v; im = j; } }
-                    for (int off = 16; off; off >>= 1) {
-                        const float ov = __shfl_xor_sync(0xffffffffu, mx, off);
-                        const int   oi = __shfl_xor_sync(0xffffffffu, im, off);
-                        if (ov > mx || (ov == mx && oi < im)) { mx = ov; im = oi; }
-                    }
-                    const int f_min = max(im - p.f_zero, 0), f_max = min(im + p.f_zero, Ndft);
-                    for (int j = f_min + lane; j < f_max; j += 32) scr[j] = 0.0f;
-                    __syncwarp();
-                    freqi[k] = im - Ndft / 2;
-                }
-                for (int i = 1; i < M;) {                               /* gnome sort, fsk.c:533-542 */
-                    if (freqi[i] >= freqi[i - 1]) ++i;
-                    else { const int t = freqi[i]; freqi[i] = freqi[i - 1]; freqi[i - 1] = t; if (i > 1) --i; }
-                }
-                for (int m = 0; m < M; ++m) tabidx[m] = freqi[m] + Ndft / 2;
-            } else {                                                    /* mask correlator, fsk.c:566-581 */
-                float cm = 0.0f; int bm = p.st;
-                for (int b = p.st + lane; b < p.en - p.len_mask; b += 32) {
-                    float corr = 0.0f;
-                    for (int i = 0; i < p.len_mask; ++i) corr = __fadd_rn(corr, __fmul_rn(s_mask[i], s_Sf[b + i]));
-                    if (corr > cm) { cm = corr; bm = b; }
-                }
-                for (int off = 16; off; off >>= 1) {
-                    const float ov = __shfl_xor_sync(0xffffffffu, cm, off);
-                    const int   ob = __shfl_xor_sync(0xffffffffu, bm, off);
-                    if (ov > cm || (ov == cm && ob < bm)) { cm = ov; bm = ob; }
-                }
-                for (int m = 0; m < M; ++m) tabidx[m] = bm * M + m;
-            }
+            int tabidx[4];
+            estimate_tones(p, s_Sf, scr, s_mask, lane, tabidx);
             PROF(2);
             /* integrator memory shift (fsk.c:637-640): source and destination never overlap (Nsym >= 4) */
             for (int e = lane; e < M * nold; e += 32) {

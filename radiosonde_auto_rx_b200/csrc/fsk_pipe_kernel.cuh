@@ -1,0 +1,437 @@
+/* fsk_pipe_kernel.cuh -- warp-specialised, software-pipelined fsk_demod frame kernel (sm_100a).
+ *
+ * Why: the per-tone local oscillator phi_c *= dphi (utils/fsk.c:646-647) is a strictly serial complex
+ * recurrence -- 4 FMUL + 2 FADD per sample that must stay un-fused and in order to be bit-exact -- and one
+ * warp issues one FP32 instruction per ~2 cycles (profiles/r01_notes.md), so ONE channel can never exceed
+ * ~1 sample per 11-14 SM cycles.  Everything else in fsk_demod_core is parallel or much shorter.  This kernel
+ * therefore makes the oscillator warp the only thing on the critical path and keeps it running without ever
+ * waiting, with four warp roles inside the channel's CTA communicating through shared-memory rings and
+ * release/acquire counters:
+ *
+ *   EST  (4 warps)  frame k+1:  windowed FFTs straight from HBM/L2 -> |X| -> Sf IIR -> tone estimate -> dphi LUT
+ *                               (needs only c_{k+1} = c_k + nin_k, which is known when frame k starts)  fsk.c:438-590
+ *   OSC  (1 warp)   frame k:    phi recurrence, one lane per tone, into a ring indexed by absolute sample
+ *                               number; never waits in steady state                                 fsk.c:644-651
+ *   CONS (2 warps)  frame k:    stream behind OSC in 64-sample blocks: x*conj(phi) in place in the ring,
+ *                               then every integrate-and-dump window that became complete            fsk.c:648,659-668
+ *   CTRL (1 warp)   frame k:    streams behind CONS: timing terms, the sequential timing accumulate, exact
+ *                               atan2f, nin/ppm, publishes frame k+1, then decisions, outputs, EbNo sums fsk.c:682-817
+ *
+ * The integrator memory of the reference (last Nmem-nin down-converted samples, fsk.c:637-640) falls out of
+ * indexing f_dc by absolute sample number: a sample is mixed exactly once, with the oscillator of the frame
+ * that first saw it, and frame k's windows start at c_{k+1}-Nmem.
+ * Used when numffts = floor(nin/(Ndft/2))-1 is the same for the three possible nin (true for every auto_rx
+ * production line); otherwise the host falls back to the serial kernel in fsk_kernel.cuh.
+ * Arithmetic, operand order and summation order are identical to fsk_kernel.cuh, hence to the reference.
+ */
+#pragma once
+#include "fsk_kernel.cuh"
+
+#define PIPE_R    1024          /* ring capacity per tone, samples (power of two, multiple of PIPE_BLK) */
+#define PIPE_BLK  64            /* consumer block / oscillator publication granularity                  */
+#define PIPE_NEST 4             /* EST warps  */
+#define PIPE_NCONS 2            /* CONS warps */
+
+struct PipeDesc {               /* per-frame descriptor, 4 slots */
+    int    c;                   /* frame start, samples relative to this call's stream start */
+    int    nin;
+    float2 dphi[4];
+    int    tabidx[4];
+    float2 phi_end[4];
+};
+
+__device__ __forceinline__ int ld_acq(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_rel(int *p, int v)
+{
+    asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+/* Warp-uniform wait: lane 0 polls `*flag >= want`, giving up when `*stop` is raised. */
+__device__ __forceinline__ bool warp_wait_ge(const int *flag, int want, const int *stop, int lane)
+{
+    int ok = 1;
+    if (lane == 0) {
+        while (ld_acq(flag) < want) {
+            if (ld_acq(stop)) { ok = (ld_acq(flag) >= want); break; }
+            __nanosleep(40);
+        }
+    }
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    __syncwarp();
+    return ok != 0;
+}
+__device__ __forceinline__ void group_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+/* n oscillator steps written to consecutive ring slots (no wrap inside a chunk); paired 16-byte stores. */
+__device__ __forceinline__ float2 osc_chunk(float2 ph, const float2 d, float2 *dst, int pos, int n)
+{
+    int j = 0;
+    if ((pos & 1) && n > 0) { ph = cmul_rn(ph, d); dst[0] = ph; j = 1; }
+#pragma unroll 4
+    for (; j + 1 < n; j += 2) {
+        const float2 a = cmul_rn(ph, d);
+        ph = cmul_rn(a, d);
+        *reinterpret_cast<float4 *>(dst + j) = make_float4(a.x, a.y, ph.x, ph.y);
+    }
+    if (j < n) { ph = cmul_rn(ph, d); dst[j] = ph; }
+    return ph;
+}
+
+__global__ void __launch_bounds__(FSK_THREADS) fsk_demod_pipe_kernel(const FskKParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ PipeDesc desc[4];
+    __shared__ int s_published, s_est_done, s_osc_pos, s_free_pos, s_fint_total, s_decide_done, s_stop;
+    __shared__ int s_frames, s_nin_state, s_high_last, s_nan_last;
+    __shared__ float s_nrt_state, s_ppm_state;
+    __shared__ float2 s_phi0[4];
+
+    const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int M = p.M, Ndft = p.Ndft, Nmem = p.Nmem, nfi = p.nfi, P = p.P, Ts = p.Ts, nsym = p.Nsym;
+    const int step = Ts / P, nin_min = p.N - Ts / 2;
+
+    float2 *ring   = (float2 *)(smem + p.q_ring);     /* [M][PIPE_R]: phi, then f_dc in place */
+    float2 *fint   = (float2 *)(smem + p.q_fint);     /* [M][nfi] */
+    float2 *fftbuf = (float2 *)(smem + p.q_fft);      /* [PIPE_NEST][Ndft] */
+    float  *magbuf = (float *)(smem + p.q_mag);       /* [PIPE_NEST][Ndft] */
+    float  *Sfbuf  = (float *)(smem + p.q_Sf);        /* [2][Ndft]: Sf after frame k lives in buffer k&1 */
+    float  *s_hann = (float *)(smem + p.q_hann);
+    float2 *s_tw   = (float2 *)(smem + p.q_tw);
+    unsigned short *s_iperm = (unsigned short *)(smem + p.q_perm);
+    float  *scr    = (float *)(smem + p.q_scr);
+    float  *s_mask = (float *)(smem + p.q_mask);
+    float2 *s_maxs = (float2 *)(smem + p.q_smax);
+    float2 *tbuf   = (float2 *)(smem + p.q_tbuf);     /* [32] timing terms of one batch */
+
+    /* ---- prologue ---- */
+    for (int i = tid; i < Ndft; i += FSK_THREADS) {
+        s_hann[i] = p.hann[i]; s_tw[i] = p.tw[i]; s_iperm[i] = p.invperm[i]; s_mask[i] = p.mask[i];
+        Sfbuf[Ndft + i] = p.Sf[(long long)c * Ndft + i];                 /* "after frame -1" -> buffer 1 */
+    }
+    for (int e = tid; e < M * p.tailcap; e += FSK_THREADS) {            /* integrator memory -> ring slots [-tailcap,0) */
+        const int m = e / p.tailcap, i = e - m * p.tailcap;
+        ring[m * PIPE_R + ((i - p.tailcap) & (PIPE_R - 1))] = p.fdc_tail[((long long)c * M + m) * p.tailcap + i];
+    }
+    const long long start = p.in_off ? (long long)p.in_off[c] : 0;
+    const long long gbase = (long long)c * p.in_stride + start;
+    const int nsamp_rel = (int)(p.nsamp - start);
+    const int fbase = p.frame_base ? p.frame_base[c] : 0;
+    if (tid < M) s_phi0[tid] = p.phi_c[c * 4 + tid];
+    if (tid == 0) {
+        const int nin0 = p.nin[c];
+        s_nin_state = nin0; s_nrt_state = p.nrt[c]; s_ppm_state = p.ppm[c];
+        s_frames = 0; s_high_last = 0; s_nan_last = 0;
+        s_est_done = 0; s_osc_pos = 0; s_free_pos = -p.tailcap; s_fint_total = 0; s_decide_done = 0;
+        const bool exists0 = nin0 <= nsamp_rel;
+        desc[0].c = 0; desc[0].nin = nin0; desc[1].c = nin0;
+        s_published = exists0 ? 1 : 0; s_stop = exists0 ? 0 : 1;
+    }
+    __syncthreads();
+
+    /* role of this warp; CTAs sharing an SM with another CTA (bid >= #SMs) rotate so the two oscillators
+       sit on different SM sub-partitions (warp id % 4) */
+    const int rw = (warp - (blockIdx.x >= 148 ? 1 : 0)) & 7;
+    unsigned char *outb = (unsigned char *)p.out + (long long)c * p.out_stride * (p.soft ? 4 : 1);
+
+    if (rw == 0) {
+        /* =========================== OSC ======================================================== */
+        float2 ph = lane < M ? s_phi0[lane] : make_float2(1.0f, 0.0f);
+        float2 *myring = ring + (lane < M ? lane : 0) * PIPE_R;
+        int pos = 0;
+        for (int k = 0;; ++k) {
+            if (!warp_wait_ge(&s_est_done, k + 1, &s_stop, lane)) break;
+            const float2 d = desc[k & 3].dphi[lane < M ? lane : 0];
+            int done = 0, target = nin_min, nin = -1;
+            bool stopped = false;
+            while (true) {
+                while (done < target) {
+                    const int n = min(PIPE_BLK - (pos & (PIPE_BLK - 1)), target - done);
+                    int ok = 1;
+                    if (lane == 0) {                                     /* ring space: slot of pos+n-1 must be free */
+                        while (pos + n - ld_acq(&s_free_pos) > PIPE_R) { if (ld_acq(&s_stop)) { ok = 0; break; } __nanosleep(40); }
+                    }
+                    ok = __shfl_sync(0xffffffffu, ok, 0);
+                    if (!ok) { stopped = true; break; }
+                    if (lane < M) ph = osc_chunk(ph, d, myring + (pos & (PIPE_R - 1)), pos, n);
+                    __syncwarp();
+                    pos += n; done += n;
+                    if (lane == 0) st_rel(&s_osc_pos, pos);
+                }
+                if (stopped || nin >= 0) break;
+                if (!warp_wait_ge(&s_published, k + 1, &s_stop, lane)) { stopped = true; break; }
+                nin = desc[k & 3].nin; target = nin;
+            }
+            if (stopped) break;
+            if (lane < M) {                                             /* comp_normalize, comp_prim.h:133-139 */
+                const float av = __fsqrt_rn(mag2_rn(ph));
+                ph = make_float2(__fdiv_rn(ph.x, av), __fdiv_rn(ph.y, av));
+                desc[k & 3].phi_end[lane] = ph;
+            }
+            __syncwarp();
+        }
+    } else if (rw == 4) {
+        /* =========================== CTRL: timing, publish, decide ================================= */
+        float nrt_state = s_nrt_state, ppm = s_ppm_state;
+        int k = 0;
+        bool exists = ld_acq(&s_published) >= 1;
+        while (exists) {
+            const int ck = desc[k & 3].c, nin = desc[k & 3].nin;
+            float acc = 0.0f;
+            for (int i0 = 0; i0 < nfi; i0 += 32) {                       /* fsk.c:686-698, streamed */
+                const int cnt = min(32, nfi - i0);
+                warp_wait_ge(&s_fint_total, k * nfi + i0 + cnt, &s_stop, lane);
+                if (lane < cnt) {
+                    const int i = i0 + lane;
+                    float ft1 = 0.0f;
+                    for (int m = 0; m < M; ++m) ft1 = __fadd_rn(ft1, mag2_rn(fint[m * nfi + i]));
+                    const float2 pf = __ldg(p.phi_ft + i);
+                    tbuf[lane] = make_float2(__fmul_rn(ft1, pf.x), __fmul_rn(ft1, pf.y));
+                }
+                __syncwarp();
+                if (lane < 2) {
+                    const float *t = (const float *)tbuf + lane;
+#pragma unroll 8
+                    for (int j = 0; j < cnt; ++j) acc = __fadd_rn(acc, t[2 * j]);
+                }
+                __syncwarp();
+            }
+            const float tr = __shfl_sync(0xffffffffu, acc, 0), ti = __shfl_sync(0xffffffffu, acc, 1);
+            int nan = 0, nin_next = nin, low = 0, high = s_high_last; float fract = 0.0f;
+            if (isnan(tr) || isnan(ti)) nan = 1;                         /* fsk.c:702-704 */
+            else {
+                const float nrt = (float)__ddiv_rn((double)em_atan2f(ti, tr), 6.283185307179586476925286766559);
+                const float rx_timing = __fmul_rn(nrt, (float)P);
+                const float d = __fsub_rn(nrt, nrt_state);
+                nrt_state = nrt;
+                if (fabsf(d) < 0.2f) {
+                    const float appm = (float)__ddiv_rn(__dmul_rn(1e6, (double)d), (double)(float)nsym);
+                    ppm = (float)__dadd_rn(__dmul_rn(.9, (double)ppm), __dmul_rn(.1, (double)appm));
+                }
+                if (nrt > 0.25f) nin_next = p.N + Ts / 2;
+                else if (nrt < -0.25f) nin_next = p.N - Ts / 2;
+                else nin_next = p.N;
+                low = (int)floorf(rx_timing); fract = __fsub_rn(rx_timing, (float)low); high = (int)ceilf(rx_timing);
+            }
+            /* publish frame k+1 as early as possible: EST(k+2) and the end of OSC(k+1) hang on it */
+            const int c_next = ck + nin;
+            const bool exists_next = (p.max_frames <= 0 || k + 1 < p.max_frames) && (c_next + nin_next <= nsamp_rel);
+            if (lane == 0) {
+                s_nin_state = nin_next; s_nrt_state = nrt_state; s_ppm_state = ppm; s_high_last = high; s_nan_last = nan;
+                if (exists_next) { desc[(k + 1) & 3].nin = nin_next; desc[(k + 2) & 3].c = c_next + nin_next; st_rel(&s_published, k + 2); }
+            }
+            /* decisions (fsk.c:751-817) */
+            const long long ofs = (long long)(fbase + k) * p.Nbits;
+            if (!nan) {
+                const float omf = __fsub_rn(1.0f, fract);
+                for (int i = lane; i < nsym; i += 32) {
+                    const int st = (i + 1) * P;
+                    float tmax[4];
+                    for (int m = 0; m < M; ++m) {
+                        const float2 a = fint[m * nfi + st + low], b = fint[m * nfi + st + high];
+                        const float2 t = make_float2(__fadd_rn(__fmul_rn(omf, a.x), __fmul_rn(fract, b.x)),
+                                                     __fadd_rn(__fmul_rn(omf, a.y), __fmul_rn(fract, b.y)));
+                        tmax[m] = mag2_rn(t);
+                    }
+                    float mx = tmax[0]; int sym = 0;
+                    for (int m = 1; m < M; ++m) if (tmax[m] > mx) { mx = tmax[m]; sym = m; }
+                    s_maxs[i] = make_float2(mx, __fsqrt_rn(mx));
+                    if (!p.soft) {
+                        if (M == 2) outb[ofs + i] = (unsigned char)(sym == 1);
+                        else { outb[ofs + 2 * i + 1] = (unsigned char)(sym & 1); outb[ofs + 2 * i] = (unsigned char)((sym & 2) >> 1); }
+                    } else {
+                        float *o = (float *)outb + ofs;
+                        for (int m = 0; m < M; ++m) tmax[m] = __fsqrt_rn(tmax[m]);
+                        if (M == 2) { const float v = __fsub_rn(tmax[0], tmax[1]); o[i] = p.softinv ? -v : v; }
+                        else {
+                            float a = -tmax[0], b = -tmax[0];
+                            a = __fadd_rn(a, tmax[1]);  b = __fadd_rn(b, -tmax[1]);
+                            a = __fadd_rn(a, -tmax[2]); b = __fadd_rn(b, tmax[2]);
+                            a = __fadd_rn(a, tmax[3]);  b = __fadd_rn(b, tmax[3]);
+                            o[2 * i + 1] = p.softinv ? -a : a; o[2 * i] = p.softinv ? -b : b;
+                        }
+                    }
+                }
+            } else {
+                for (int i = lane; i < p.Nbits; i += 32) {
+                    if (p.soft) {
+                        float *o = (float *)outb;
+                        const float prev = (fbase + k) > 0 ? o[ofs - p.Nbits + i] : __uint_as_float(p.last_out[(long long)c * p.Nbits + i]);
+                        o[ofs + i] = p.softinv ? -prev : prev;
+                    } else {
+                        outb[ofs + i] = (fbase + k) > 0 ? outb[ofs - p.Nbits + i] : (unsigned char)p.last_out[(long long)c * p.Nbits + i];
+                    }
+                }
+            }
+            __syncwarp();
+            /* EbNo sums (fsk.c:808-815): sequential, lanes 0 (sum of max) and 1 (sum of sqrt(max)) */
+            float es = 0.0f;
+            if (lane < 2 && !nan) {
+                const float *t = (const float *)s_maxs + lane;
+#pragma unroll 4
+                for (int i = 0; i < nsym; ++i) es = __fadd_rn(es, t[2 * i]);
+            }
+            const float mean_sum = __shfl_sync(0xffffffffu, es, 1);
+            if (lane == 0) {
+                if (p.write_recs) {
+                    FskFrameRec r;
+                    r.nin_used = nin; r.nin_next = nin_next; r.norm_rx_timing = nrt_state; r.ppm = ppm;
+                    r.mean_sum = mean_sum; r.std_sum = es; r.nanflag = nan; r.high_sample = high;
+                    for (int m = 0; m < 4; ++m) r.tabidx[m] = m < M ? desc[k & 3].tabidx[m] : 0;
+                    p.recs[(long long)c * p.rec_stride + fbase + k] = r;
+                }
+                s_frames = k + 1;
+                __threadfence_block();
+                st_rel(&s_decide_done, k + 1);
+                if (!exists_next) st_rel(&s_stop, 1);
+            }
+            __syncwarp();
+            exists = exists_next; ++k;
+        }
+    } else if (rw >= 6) {
+        /* =========================== CONS: down-convert + integrate, streaming ===================== */
+        const int ct = (rw - 6) * 32 + lane, NCT = PIPE_NCONS * 32;
+        for (int k = 0;; ++k) {
+            if (!warp_wait_ge(&s_published, k + 1, &s_stop, lane)) break;
+            if (!warp_wait_ge(&s_decide_done, k, &s_stop, lane)) break;
+            const int ck = desc[k & 3].c, nin = desc[k & 3].nin, base = ck + nin - Nmem, fend = ck + nin;
+            int i_done = 0; bool stopped = false;
+            for (int s0 = ck; s0 < fend; s0 += PIPE_BLK) {
+                const int cnt = min(PIPE_BLK, fend - s0);
+                float2 xv = make_float2(0.0f, 0.0f);
+                if (ct < cnt) xv = load_sample(p.in, p.fmt, gbase + s0 + ct);
+                if (!warp_wait_ge(&s_osc_pos, s0 + cnt, &s_stop, lane)) { stopped = true; }
+                /* both CONS warps must take the same exit: agree through the group barrier below only if not stopped.
+                   s_stop is raised only after the last existing frame is fully consumed, so a stop seen here means
+                   this frame does not exist -- cannot happen for a published frame; kept for safety. */
+                if (stopped) break;
+                if (ct < cnt) {
+                    const int slot = (s0 + ct) & (PIPE_R - 1);
+                    for (int m = 0; m < M; ++m) {
+                        const float2 ph = ring[m * PIPE_R + slot];
+                        ring[m * PIPE_R + slot] = cmul_rn(xv, make_float2(ph.x, -ph.y));       /* fsk.c:648 */
+                    }
+                }
+                group_bar(2, NCT);
+                const int mixed_end = s0 + cnt;
+                int i_hi = 0;
+                if (mixed_end - base >= Ts) i_hi = min(nfi, (mixed_end - base - Ts) / step + 1);
+                const int ni = i_hi - i_done;
+                for (int e = ct; e < M * ni; e += NCT) {                 /* fsk.c:660-668 */
+                    const int m = e / ni, i = i_done + (e - m * ni);
+                    const float2 *rg = ring + m * PIPE_R;
+                    const int a0 = base + i * step;
+                    float2 acc = make_float2(0.0f, 0.0f);
+                    for (int j = 0; j < Ts; ++j) acc = cadd_rn(acc, rg[(a0 + j) & (PIPE_R - 1)]);
+                    fint[m * nfi + i] = acc;
+                }
+                group_bar(2, NCT);
+                if (ct == 0) {
+                    st_rel(&s_fint_total, k * nfi + i_hi);
+                    st_rel(&s_free_pos, min(base + i_hi * step, fend - p.tailcap));
+                }
+                i_done = i_hi;
+            }
+            if (stopped) break;
+        }
+    } else {
+        /* =========================== EST: FFTs -> Sf -> tone estimate, one frame ahead =============== */
+        const int ew = (rw <= 3) ? rw - 1 : 3;                           /* rw in {1,2,3,5} -> 0..3 */
+        const int et = ew * 32 + lane, NET = PIPE_NEST * 32;
+        const int numffts = (int)floorf(__fdiv_rn((float)nin_min, (float)(Ndft / 2))) - 1;   /* same for all 3 nin (host-checked) */
+        float2 *F = fftbuf + ew * Ndft;
+        for (int k = 0;; ++k) {
+            if (!warp_wait_ge(&s_published, k, &s_stop, lane)) break;
+            const int ck = desc[k & 3].c;
+            if (!(ck + nin_min <= nsamp_rel && (p.max_frames <= 0 || k < p.max_frames))) break;   /* frame k cannot exist */
+            const float *Sf_in = Sfbuf + ((k + 1) & 1) * Ndft;
+            float *Sf_out = Sfbuf + (k & 1) * Ndft;
+            if (numffts <= 0) { for (int i = et; i < Ndft; i += NET) Sf_out[i] = Sf_in[i]; group_bar(1, NET); }
+            for (int r0 = 0; r0 < numffts; r0 += PIPE_NEST) {
+                const int j = r0 + ew;
+                if (j < numffts) {
+                    const long long a = gbase + ck + j * (Ndft / 2);
+                    for (int i = lane; i < Ndft; i += 32) {              /* fsk.c:470-478, coalesced read, scatter to DIT order */
+                        const float2 v = load_sample(p.in, p.fmt, a + i);
+                        const float h = s_hann[i];
+                        F[s_iperm[i]] = make_float2(__fmul_rn(h, v.x), __fmul_rn(h, v.y));
+                    }
+                    __syncwarp();
+                    warp_fft(F, s_tw, p, lane);
+                    for (int i = lane; i < Ndft; i += 32) magbuf[ew * Ndft + i] = __fsqrt_rn(mag2_rn(F[i]));
+                }
+                group_bar(1, NET);
+                const int cnt = min(PIPE_NEST, numffts - r0);
+                for (int i = et; i < Ndft; i += NET) {
+                    float s = (r0 == 0) ? Sf_in[i] : Sf_out[i];
+                    const int src = (i + Ndft / 2) & (Ndft - 1);
+                    for (int jj = 0; jj < cnt; ++jj)
+                        s = __fadd_rn(__fmul_rn(s, p.omtc), __fmul_rn(magbuf[jj * Ndft + src], p.tc));    /* fsk.c:500 */
+                    Sf_out[i] = s;
+                }
+                group_bar(1, NET);
+            }
+            if (ew == 0) {
+                int tabidx[4];
+                estimate_tones(p, Sf_out, scr, s_mask, lane, tabidx);
+                if (lane < M) { const int ti = tabidx[lane]; desc[k & 3].tabidx[lane] = ti; desc[k & 3].dphi[lane] = __ldg(p.dphi_tab + ti); }
+                __syncwarp();
+                if (lane == 0) st_rel(&s_est_done, k + 1);
+            }
+        }
+    }
+    __syncthreads();
+
+    /* ---- epilogue: state back to HBM ---- */
+    const int frames = s_frames;
+    const int c_end = frames > 0 ? desc[frames & 3].c : 0;             /* desc[k+1].c is written when frame k is published */
+    const float *Sf_fin = Sfbuf + ((frames + 1) & 1) * Ndft;            /* buffer (frames-1)&1 */
+    for (int i = tid; i < Ndft; i += FSK_THREADS) p.Sf[(long long)c * Ndft + i] = Sf_fin[i];
+    for (int e = tid; e < M * p.tailcap; e += FSK_THREADS) {
+        const int m = e / p.tailcap, i = e - m * p.tailcap;
+        p.fdc_tail[((long long)c * M + m) * p.tailcap + i] = ring[m * PIPE_R + ((c_end - p.tailcap + i) & (PIPE_R - 1))];
+    }
+    if (tid < M) p.phi_c[c * 4 + tid] = frames > 0 ? desc[(frames - 1) & 3].phi_end[tid] : s_phi0[tid];
+    if (tid == 0) {
+        p.nin[c] = s_nin_state; p.nrt[c] = s_nrt_state; p.ppm[c] = s_ppm_state;
+        p.nframes[c] = fbase + frames; p.consumed[c] = c_end;
+        p.tot_frames[c] += frames; p.tot_samples[c] += c_end;
+        if (p.frame_base) p.frame_base[c] = fbase + frames;
+    }
+    if (frames > 0) {
+        const long long ofs = (long long)(fbase + frames - 1) * p.Nbits;
+        for (int i = tid; i < p.Nbits; i += FSK_THREADS)
+            p.last_out[(long long)c * p.Nbits + i] = p.soft ? __float_as_uint(((const float *)outb)[ofs + i]) : (unsigned int)outb[ofs + i];
+        if (p.write_recs && !s_nan_last) {
+            const int neyeoffset = s_high_last + 1, tot = p.eye_traces * M * p.neyesamp;
+            for (int e = tid; e < tot; e += FSK_THREADS) {
+                const int row = e / p.neyesamp, j = e - row * p.neyesamp, i = row / M, m = row - i * M;
+                const int ind = 2 * P * i + neyeoffset + j * p.eye_dec, flat = m * nfi + ind;
+                float2 v = make_float2(0.0f, 0.0f);
+                if (flat >= 0 && ind < nfi) v = fint[flat];
+                p.eye_raw[(long long)c * (8 * 160) + row * 160 + j] = __fsqrt_rn(mag2_rn(v));
+            }
+        }
+    }
+    if (p.carry_cap > 0) {                                             /* same tail carry as the serial kernel */
+        const long long cursor = start + c_end, tail = p.nsamp - cursor;
+        const int es = p.fmt == 1 ? 8 : (p.fmt == 0 ? 4 : 2);
+        const long long nhalf = tail * es / 2;
+        const int chunk = (int)(p.q_stage_bytes / 2);
+        unsigned short *stage = (unsigned short *)(smem + p.q_fint);    /* f_int is dead now (eye already written) */
+        const long long base = (long long)c * p.in_stride;
+        const unsigned short *src = (const unsigned short *)((const unsigned char *)p.in + (base + cursor) * es);
+        unsigned short *dst = (unsigned short *)((unsigned char *)p.carry_dst + (base + p.carry_cap - tail) * es);
+        for (long long k0 = 0; k0 < nhalf; k0 += chunk) {
+            const int n = (int)min((long long)chunk, nhalf - k0);
+            __syncthreads();
+            for (int i = tid; i < n; i += FSK_THREADS) stage[i] = src[k0 + i];
+            __syncthreads();
+            for (int i = tid; i < n; i += FSK_THREADS) dst[k0 + i] = stage[i];
+        }
+        if (tid == 0) p.in_off_next[c] = (int)(p.carry_cap - tail);
+    }
+}

@@ -21,9 +21,19 @@ CONFIGS = {
 }
 
 
-def make_batch(cfg: po.FskConfig, nchan: int, device: int = 0) -> fsk.FskBatch:
-    return fsk.FskBatch(cfg.Fs, cfg.Rs, cfg.M, cfg.P, cfg.Nsym, 1000, cfg.fs_tx, cfg.lo, cfg.hi, 1 if cfg.mask else 0,
-                        nchan=nchan, device=device)
+def make_batch(cfg: po.FskConfig, nchan: int, device: int = 0, mode: str | None = None) -> fsk.FskBatch:
+    """mode 'serial' forces the one-stage-at-a-time kernel; default lets the library pick (pipelined when eligible)."""
+    import os
+    old = os.environ.pop("B200FSK_KERNEL", None)
+    if mode:
+        os.environ["B200FSK_KERNEL"] = mode
+    try:
+        return fsk.FskBatch(cfg.Fs, cfg.Rs, cfg.M, cfg.P, cfg.Nsym, 1000, cfg.fs_tx, cfg.lo, cfg.hi, 1 if cfg.mask else 0,
+                            nchan=nchan, device=device)
+    finally:
+        os.environ.pop("B200FSK_KERNEL", None)
+        if old is not None:
+            os.environ["B200FSK_KERNEL"] = old
 
 
 def channels(seed, nchan, nsamp, kw):
@@ -33,12 +43,13 @@ def channels(seed, nchan, nsamp, kw):
     return iq
 
 
+@pytest.mark.parametrize("mode", ["auto", "serial"])
 @pytest.mark.parametrize("name", list(CONFIGS))
-def test_push_matches_oracle(cuda, name):
+def test_push_matches_oracle(cuda, name, mode):
     cfg, kw = CONFIGS[name]
     nchan, nsamp = 5, 150_000
     iq = channels(100 + len(name), nchan, nsamp, kw)
-    b = make_batch(cfg, nchan)
+    b = make_batch(cfg, nchan, mode=None if mode == "auto" else mode)
     b.enable_stats(True)
     out, frames = b.push(iq, "cs16", soft=cfg.soft, softinv=cfg.softinv)
     for c in range(nchan):
@@ -59,13 +70,14 @@ def test_push_matches_oracle(cuda, name):
         assert b.Sf(c).tobytes() == orc.Sf().tobytes()
 
 
-def test_chunked_push_equals_single_push(cuda):
+@pytest.mark.parametrize("mode", ["auto", "serial"])
+def test_chunked_push_equals_single_push(cuda, mode):
     """Streaming: arbitrary chunking of the input must not change a single output bit (carry logic)."""
     cfg = po.RS41
     nchan, nsamp = 3, 100_000
     iq = channels(7, nchan, nsamp, {})
     ref = [po.Oracle(cfg).run_stream(iq[c])[0] for c in range(nchan)]
-    b = make_batch(cfg, nchan)
+    b = make_batch(cfg, nchan, mode=None if mode == "auto" else mode)
     rng = np.random.default_rng(5)
     pos, got = 0, [[] for _ in range(nchan)]
     while pos < nsamp:
