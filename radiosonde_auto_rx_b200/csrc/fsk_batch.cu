@@ -86,6 +86,16 @@ static int plan_fft(int n, FskKParams &kp, std::vector<unsigned short> &perm)
     return 0;
 }
 
+/* the pipelined kernel is specialised on tone count and input sample format */
+typedef void (*pipe_fn_t)(const FskKParams);
+static const void *pipe_kernel_fn(int M, int fmt)
+{
+    static const pipe_fn_t tab[2][4] = {
+        {fsk_demod_pipe_kernel<2, 0>, fsk_demod_pipe_kernel<2, 1>, fsk_demod_pipe_kernel<2, 2>, fsk_demod_pipe_kernel<2, 3>},
+        {fsk_demod_pipe_kernel<4, 0>, fsk_demod_pipe_kernel<4, 1>, fsk_demod_pipe_kernel<4, 2>, fsk_demod_pipe_kernel<4, 3>}};
+    return (const void *)tab[M == 4 ? 1 : 0][fmt & 3];
+}
+
 template <class T> static cudaError_t upload(T **dptr, const std::vector<T> &v)
 {
     cudaError_t e = cudaMalloc((void **)dptr, v.size() * sizeof(T));
@@ -201,13 +211,13 @@ extern "C" int b200fsk_create(b200fsk_t **out, const b200fsk_cfg_t *cfg, int nch
         const int f0 = (int)floor((float)nmin / (Ndft / 2)), f1 = (int)floor((float)nmax / (Ndft / 2));
         size_t q = 0;
         auto takeq = [&](size_t bytes) { size_t r = q; q += (bytes + 15) & ~(size_t)15; return (int)r; };
-        kp.q_ring = takeq((size_t)M * PIPE_R * 8); kp.q_fint = takeq((size_t)M * nfi * 8); kp.q_stage_bytes = M * nfi * 8;
-        kp.q_fft = takeq((size_t)PIPE_NEST * Ndft * 8); kp.q_mag = takeq((size_t)PIPE_NEST * Ndft * 4);
+        kp.q_ring = takeq((size_t)M * PIPE_R * 8); kp.q_fint = takeq((size_t)2 * M * nfi * 8); kp.q_stage_bytes = 2 * M * nfi * 8;
+        kp.q_fft = takeq((size_t)PIPE_NEST * (Ndft + Ndft / 8) * 8); kp.q_mag = takeq((size_t)(f0 > 1 ? f0 - 1 : 1) * Ndft * 4);
         kp.q_Sf = takeq((size_t)2 * Ndft * 4); kp.q_hann = takeq(Ndft * 4); kp.q_tw = takeq(Ndft * 8); kp.q_perm = takeq(Ndft * 2);
-        kp.q_scr = takeq(Ndft * 4); kp.q_mask = takeq(Ndft * 4); kp.q_smax = takeq((size_t)Nsym * 8); kp.q_tbuf = takeq(32 * 8);
+        kp.q_scr = takeq(Ndft * 4); kp.q_mask = takeq(Ndft * 4); kp.q_smax = takeq((size_t)Nsym * 8); kp.q_tbuf = takeq(PIPE_TB * 8);
         h->smem_pipe = q;
         const char *force = getenv("B200FSK_KERNEL");
-        h->use_pipe = (f0 == f1) && (f0 - 1 >= 1) && (3 * Ts + 2 * PIPE_BLK + 16 <= PIPE_R) && (Ts % 2 == 0 || true) &&
+        h->use_pipe = (f0 == f1) && (f0 - 1 >= 1) && (3 * Ts + 2 * PIPE_BLK + 16 <= PIPE_R) && (nfi >= 2) && (Ndft <= 256) && (Ts % 2 == 0 || true) &&
                       (h->smem_pipe + 1024 <= (size_t)227 * 1024);
         if (force && !strcmp(force, "serial")) h->use_pipe = false;
     }
@@ -215,7 +225,12 @@ extern "C" int b200fsk_create(b200fsk_t **out, const b200fsk_cfg_t *cfg, int nch
     CK(cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     if (h->smem + 256 > (size_t)maxsmem) { delete h; return fail(B200FSK_ENOMEM, "frame working set %zu B exceeds shared memory %d B", h->smem, maxsmem); }
     CK(cudaFuncSetAttribute(fsk_demod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-    if (h->use_pipe) CK(cudaFuncSetAttribute(fsk_demod_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_pipe));
+    if (h->use_pipe) {
+        for (int f = 0; f < 4; ++f) {
+            const void *fn = pipe_kernel_fn(M, f);
+            CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_pipe));
+        }
+    }
 
     std::vector<unsigned short> invperm(Ndft);
     for (int pos = 0; pos < Ndft; ++pos) invperm[perm[pos]] = (unsigned short)pos;
@@ -325,8 +340,10 @@ static int flush_pending(b200fsk *h)
 static int launch(b200fsk *h, FskKParams &kp, cudaStream_t s, bool time_it)
 {
     if (time_it) CK(cudaEventRecord(h->ev0, s));
-    if (h->use_pipe) fsk_demod_pipe_kernel<<<h->nchan, FSK_THREADS, h->smem_pipe, s>>>(kp);
-    else fsk_demod_kernel<<<h->nchan, FSK_THREADS, h->smem, s>>>(kp);
+    if (h->use_pipe) {
+        void *args[] = {(void *)&kp};
+        CK(cudaLaunchKernel(pipe_kernel_fn(kp.M, kp.fmt), dim3(h->nchan), dim3(PIPE_THREADS), args, h->smem_pipe, s));
+    } else fsk_demod_kernel<<<h->nchan, FSK_THREADS, h->smem, s>>>(kp);
     CK(cudaGetLastError());
     if (time_it) { CK(cudaEventRecord(h->ev1, s)); h->timed = true; }
     h->launches++;

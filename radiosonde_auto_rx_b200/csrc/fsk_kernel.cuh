@@ -96,36 +96,60 @@ __device__ __forceinline__ float2 load_sample(const void *in, int fmt, long long
     return make_float2(__fdiv_rn((float)s, 1000.0f), 0.0f);
 }
 
+template <int FMT> __device__ __forceinline__ float2 load_sample_t(const void *in, long long idx)
+{
+    if (FMT == 1) return __ldg((const float2 *)in + idx);
+    if (FMT == 0) {
+        const short2 s = __ldg((const short2 *)in + idx);
+        return make_float2(__fdiv_rn((float)s.x, 1000.0f), __fdiv_rn((float)s.y, 1000.0f));
+    }
+    if (FMT == 2) {
+        const uchar2 u = __ldg((const uchar2 *)in + idx);
+        return make_float2(__fdiv_rn(__fsub_rn((float)u.x, 127.0f), 128.0f), __fdiv_rn(__fsub_rn((float)u.y, 127.0f), 128.0f));
+    }
+    const short s = __ldg((const short *)in + idx);
+    return make_float2(__fdiv_rn((float)s, 1000.0f), 0.0f);
+}
+
 /* In-place mixed-radix DIT FFT of one warp's buffer; F already holds the permuted, windowed input.
  * Same butterflies, twiddle indices and operand order as kiss_fft's kf_bfly2 / kf_bfly4 forward
- * (kiss_fft.c:21-42, 44-90), executed stage by stage bottom-up. */
+ * (kiss_fft.c:21-42, 44-90), executed stage by stage bottom-up.  PAD inserts one float2 of padding per 8
+ * elements (index i -> i + i/8) so that the stride-8/stride-32 butterfly stages do not bank-conflict. */
+template <bool PAD> __device__ __forceinline__ int fpad(int i) { return PAD ? i + (i >> 3) : i; }
+
+template <bool PAD>
 __device__ __forceinline__ void warp_fft(float2 *F, const float2 *tw, const FskKParams &p, int lane)
 {
-    const int n = p.Ndft;
+    const int lgn = 31 - __clz(p.Ndft);
+#pragma unroll 1
     for (int st = p.nstage - 1; st >= 0; --st) {
         const int radix = p.radix[st], lm = p.log2m[st], m = 1 << lm, fs = p.fstride[st];
-        const int nb = n / radix;
+        const int lr = (radix == 2) ? 1 : 2;
+        const int nb = 1 << (lgn - lr);
+#pragma unroll 1
         for (int b = lane; b < nb; b += 32) {
             const int blk = b >> lm, u = b & (m - 1);
-            float2 *X = F + blk * radix * m + u;
+            const int i0 = (blk << (lm + lr)) + u;
             if (radix == 2) {
-                const float2 t = cmul_rn(X[m], tw[fs * u]);
-                const float2 x0 = X[0];
-                X[m] = csub_rn(x0, t);
-                X[0] = cadd_rn(x0, t);
+                float2 *X0 = F + fpad<PAD>(i0), *X1 = F + fpad<PAD>(i0 + m);
+                const float2 t = cmul_rn(*X1, tw[fs * u]);
+                const float2 x0 = *X0;
+                *X1 = csub_rn(x0, t);
+                *X0 = cadd_rn(x0, t);
             } else {
-                const float2 s0 = cmul_rn(X[m], tw[fs * u]);
-                const float2 s1 = cmul_rn(X[2 * m], tw[fs * u * 2]);
-                const float2 s2 = cmul_rn(X[3 * m], tw[fs * u * 3]);
-                const float2 x0 = X[0];
+                float2 *X0 = F + fpad<PAD>(i0), *X1 = F + fpad<PAD>(i0 + m), *X2 = F + fpad<PAD>(i0 + 2 * m), *X3 = F + fpad<PAD>(i0 + 3 * m);
+                const float2 s0 = cmul_rn(*X1, tw[fs * u]);
+                const float2 s1 = cmul_rn(*X2, tw[fs * u * 2]);
+                const float2 s2 = cmul_rn(*X3, tw[fs * u * 3]);
+                const float2 x0 = *X0;
                 const float2 s5 = csub_rn(x0, s1);
                 const float2 a  = cadd_rn(x0, s1);
                 const float2 s3 = cadd_rn(s0, s2);
                 const float2 s4 = csub_rn(s0, s2);
-                X[2 * m] = csub_rn(a, s3);
-                X[0]     = cadd_rn(a, s3);
-                X[m]     = make_float2(__fadd_rn(s5.x, s4.y), __fsub_rn(s5.y, s4.x));
-                X[3 * m] = make_float2(__fsub_rn(s5.x, s4.y), __fadd_rn(s5.y, s4.x));
+                *X2 = csub_rn(a, s3);
+                *X0 = cadd_rn(a, s3);
+                *X1 = make_float2(__fadd_rn(s5.x, s4.y), __fsub_rn(s5.y, s4.x));
+                *X3 = make_float2(__fsub_rn(s5.x, s4.y), __fadd_rn(s5.y, s4.x));
             }
         }
         __syncwarp();
@@ -249,7 +273,7 @@ __global__ void __launch_bounds__(FSK_THREADS) fsk_demod_kernel(const FskKParams
                     F[pos] = make_float2(__fmul_rn(h, v.x), __fmul_rn(h, v.y));
                 }
                 __syncwarp();
-                warp_fft(F, s_tw, p, lane);
+                warp_fft<false>(F, s_tw, p, lane);
                 for (int i = lane; i < Ndft; i += 32) magbuf[warp * Ndft + i] = __fsqrt_rn(mag2_rn(F[i]));
             }
             __syncthreads();

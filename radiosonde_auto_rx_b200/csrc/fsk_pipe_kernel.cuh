@@ -8,14 +8,15 @@
  * waiting, with four warp roles inside the channel's CTA communicating through shared-memory rings and
  * release/acquire counters:
  *
- *   EST  (4 warps)  frame k+1:  windowed FFTs straight from HBM/L2 -> |X| -> Sf IIR -> tone estimate -> dphi LUT
+ *   EST  (5 warps)  frame k+1:  windowed FFTs straight from HBM/L2 -> |X| -> Sf IIR -> tone estimate -> dphi LUT
  *                               (needs only c_{k+1} = c_k + nin_k, which is known when frame k starts)  fsk.c:438-590
  *   OSC  (1 warp)   frame k:    phi recurrence, one lane per tone, into a ring indexed by absolute sample
  *                               number; never waits in steady state                                 fsk.c:644-651
- *   CONS (2 warps)  frame k:    stream behind OSC in 64-sample blocks: x*conj(phi) in place in the ring,
+ *   CONS (4 warps)  frame k:    stream behind OSC in 128-sample blocks: x*conj(phi) in place in the ring,
  *                               then every integrate-and-dump window that became complete            fsk.c:648,659-668
- *   CTRL (1 warp)   frame k:    streams behind CONS: timing terms, the sequential timing accumulate, exact
- *                               atan2f, nin/ppm, publishes frame k+1, then decisions, outputs, EbNo sums fsk.c:682-817
+ *   TIME (1 warp)   frame k:    streams behind CONS: timing terms, the sequential timing accumulate, exact
+ *                               atan2f, nin/ppm, publishes frame k+1                                 fsk.c:682-731
+ *   DEC  (1 warp)   frame k:    re-sample + decide + outputs to HBM, sequential EbNo sums, frame record fsk.c:737-817
  *
  * The integrator memory of the reference (last Nmem-nin down-converted samples, fsk.c:637-640) falls out of
  * indexing f_dc by absolute sample number: a sample is mixed exactly once, with the oscillator of the frame
@@ -27,10 +28,26 @@
 #pragma once
 #include "fsk_kernel.cuh"
 
+#ifdef FSK_PROFILE
+#define PTIC long long pt_ = clock64();
+#define PTOC(a) do { pacc[a] += clock64() - pt_; } while (0)
+#define PDECL long long pacc[4] = {0, 0, 0, 0}; const long long prole0_ = clock64();
+#define PFLUSH(base, n) do { if (lane == 0 && p.prof) { for (int q_ = 0; q_ < (n); ++q_) p.prof[blockIdx.x * 16 + (base) + q_] += pacc[q_]; p.prof[blockIdx.x * 16 + (base) + (n)] += clock64() - prole0_; } } while (0)
+#else
+#define PTIC
+#define PTOC(a)
+#define PDECL
+#define PFLUSH(base, n)
+#endif
+
+#define PIPE_THREADS 384        /* 12 warps: OSC 1, TIME 1, DEC 1, CONS 4, EST 5 */
 #define PIPE_R    1024          /* ring capacity per tone, samples (power of two, multiple of PIPE_BLK) */
-#define PIPE_BLK  64            /* consumer block / oscillator publication granularity                  */
-#define PIPE_NEST 4             /* EST warps  */
-#define PIPE_NCONS 2            /* CONS warps */
+#define PIPE_BLK  128           /* consumer block / oscillator publication granularity                  */
+#define PIPE_NEST 5             /* EST warps  */
+#define PIPE_NCONS 4            /* CONS warps */
+#define PIPE_TB   64            /* timing terms per batch */
+
+enum { ROLE_OSC = 0, ROLE_TIME, ROLE_DEC, ROLE_CONS, ROLE_EST };
 
 struct PipeDesc {               /* per-frame descriptor, 4 slots */
     int    c;                   /* frame start, samples relative to this call's stream start */
@@ -38,6 +55,9 @@ struct PipeDesc {               /* per-frame descriptor, 4 slots */
     float2 dphi[4];
     int    tabidx[4];
     float2 phi_end[4];
+    /* timing result of the frame (TIME -> DEC) */
+    int    nan, low, high, nin_next, exists_next;
+    float  fract, nrt, ppm;
 };
 
 __device__ __forceinline__ int ld_acq(const int *p)
@@ -51,13 +71,13 @@ __device__ __forceinline__ void st_rel(int *p, int v)
     asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
 /* Warp-uniform wait: lane 0 polls `*flag >= want`, giving up when `*stop` is raised. */
-__device__ __forceinline__ bool warp_wait_ge(const int *flag, int want, const int *stop, int lane)
+__device__ __forceinline__ bool warp_wait_ge(const int *flag, int want, const int *stop, int lane, unsigned ns = 200)
 {
     int ok = 1;
     if (lane == 0) {
         while (ld_acq(flag) < want) {
             if (ld_acq(stop)) { ok = (ld_acq(flag) >= want); break; }
-            __nanosleep(40);
+            __nanosleep(ns);
         }
     }
     ok = __shfl_sync(0xffffffffu, ok, 0);
@@ -66,38 +86,37 @@ __device__ __forceinline__ bool warp_wait_ge(const int *flag, int want, const in
 }
 __device__ __forceinline__ void group_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-/* n oscillator steps written to consecutive ring slots (no wrap inside a chunk); paired 16-byte stores. */
-__device__ __forceinline__ float2 osc_chunk(float2 ph, const float2 d, float2 *dst, int pos, int n)
+/* n oscillator steps (n even, dst 16-byte aligned) written to consecutive ring slots; paired 16-byte stores. */
+__device__ __forceinline__ float2 osc_pairs(float2 ph, const float2 d, float2 *dst, int n)
 {
-    int j = 0;
-    if ((pos & 1) && n > 0) { ph = cmul_rn(ph, d); dst[0] = ph; j = 1; }
 #pragma unroll 4
-    for (; j + 1 < n; j += 2) {
+    for (int j = 0; j < n; j += 2) {
         const float2 a = cmul_rn(ph, d);
         ph = cmul_rn(a, d);
         *reinterpret_cast<float4 *>(dst + j) = make_float4(a.x, a.y, ph.x, ph.y);
     }
-    if (j < n) { ph = cmul_rn(ph, d); dst[j] = ph; }
     return ph;
 }
 
-__global__ void __launch_bounds__(FSK_THREADS) fsk_demod_pipe_kernel(const FskKParams p)
+template <int M, int FMT>
+__global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const FskKParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ PipeDesc desc[4];
-    __shared__ int s_published, s_est_done, s_osc_pos, s_free_pos, s_fint_total, s_decide_done, s_stop;
+    __shared__ int s_published, s_est_done, s_osc_pos, s_free_pos, s_fint_total, s_time_done, s_decide_done, s_stop;
     __shared__ int s_frames, s_nin_state, s_high_last, s_nan_last;
     __shared__ float s_nrt_state, s_ppm_state;
     __shared__ float2 s_phi0[4];
 
     const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int M = p.M, Ndft = p.Ndft, Nmem = p.Nmem, nfi = p.nfi, P = p.P, Ts = p.Ts, nsym = p.Nsym;
+    const int Ndft = p.Ndft, Nmem = p.Nmem, nfi = p.nfi, P = p.P, Ts = p.Ts, nsym = p.Nsym;
     const int step = Ts / P, nin_min = p.N - Ts / 2;
+    constexpr int lgM = (M == 2) ? 1 : 2;
 
     float2 *ring   = (float2 *)(smem + p.q_ring);     /* [M][PIPE_R]: phi, then f_dc in place */
-    float2 *fint   = (float2 *)(smem + p.q_fint);     /* [M][nfi] */
+    float2 *fintb  = (float2 *)(smem + p.q_fint);     /* [2][M][nfi]: frame k uses buffer k&1 */
     float2 *fftbuf = (float2 *)(smem + p.q_fft);      /* [PIPE_NEST][Ndft] */
-    float  *magbuf = (float *)(smem + p.q_mag);       /* [PIPE_NEST][Ndft] */
+    float  *magbuf = (float *)(smem + p.q_mag);       /* [numffts][Ndft]: |X| of every window of one frame */
     float  *Sfbuf  = (float *)(smem + p.q_Sf);        /* [2][Ndft]: Sf after frame k lives in buffer k&1 */
     float  *s_hann = (float *)(smem + p.q_hann);
     float2 *s_tw   = (float2 *)(smem + p.q_tw);
@@ -105,14 +124,15 @@ __global__ void __launch_bounds__(FSK_THREADS) fsk_demod_pipe_kernel(const FskKP
     float  *scr    = (float *)(smem + p.q_scr);
     float  *s_mask = (float *)(smem + p.q_mask);
     float2 *s_maxs = (float2 *)(smem + p.q_smax);
-    float2 *tbuf   = (float2 *)(smem + p.q_tbuf);     /* [32] timing terms of one batch */
+    float2 *tbuf   = (float2 *)(smem + p.q_tbuf);     /* [PIPE_TB] timing terms of one batch */
 
     /* ---- prologue ---- */
-    for (int i = tid; i < Ndft; i += FSK_THREADS) {
+#pragma unroll 1
+    for (int i = tid; i < Ndft; i += PIPE_THREADS) {
         s_hann[i] = p.hann[i]; s_tw[i] = p.tw[i]; s_iperm[i] = p.invperm[i]; s_mask[i] = p.mask[i];
         Sfbuf[Ndft + i] = p.Sf[(long long)c * Ndft + i];                 /* "after frame -1" -> buffer 1 */
     }
-    for (int e = tid; e < M * p.tailcap; e += FSK_THREADS) {            /* integrator memory -> ring slots [-tailcap,0) */
+    for (int e = tid; e < M * p.tailcap; e += PIPE_THREADS) {           /* integrator memory -> ring slots [-tailcap,0) */
         const int m = e / p.tailcap, i = e - m * p.tailcap;
         ring[m * PIPE_R + ((i - p.tailcap) & (PIPE_R - 1))] = p.fdc_tail[((long long)c * M + m) * p.tailcap + i];
     }
@@ -125,25 +145,42 @@ __global__ void __launch_bounds__(FSK_THREADS) fsk_demod_pipe_kernel(const FskKP
         const int nin0 = p.nin[c];
         s_nin_state = nin0; s_nrt_state = p.nrt[c]; s_ppm_state = p.ppm[c];
         s_frames = 0; s_high_last = 0; s_nan_last = 0;
-        s_est_done = 0; s_osc_pos = 0; s_free_pos = -p.tailcap; s_fint_total = 0; s_decide_done = 0;
+        s_est_done = 0; s_osc_pos = 0; s_free_pos = -p.tailcap; s_fint_total = 0; s_time_done = 0; s_decide_done = 0;
         const bool exists0 = nin0 <= nsamp_rel;
         desc[0].c = 0; desc[0].nin = nin0; desc[1].c = nin0;
         s_published = exists0 ? 1 : 0; s_stop = exists0 ? 0 : 1;
     }
     __syncthreads();
 
-    /* role of this warp; CTAs sharing an SM with another CTA (bid >= #SMs) rotate so the two oscillators
-       sit on different SM sub-partitions (warp id % 4) */
-    const int rw = (warp - (blockIdx.x >= 148 ? 1 : 0)) & 7;
+    /* Warp roles.  SM sub-partition = warp id % 4: the oscillator shares its sub-partition only with the two
+       light roles (TIME, DEC).  CTAs that share an SM with another CTA (bid >= #SMs) rotate by one warp so the
+       two oscillators sit on different sub-partitions. */
+    const int rw = (warp + 12 - (blockIdx.x >= 148 ? 1 : 0)) % 12;
+    int role, ridx;                                                     /* ridx: index inside the role's group */
+    switch (rw) {      /* sub-partition 0: OSC, DEC, TIME | 1: CONS x3 | 2: EST x3 | 3: EST x2, CONS */
+        case 0: role = ROLE_OSC; ridx = 0; break;
+        case 4: role = ROLE_DEC; ridx = 0; break;
+        case 8: role = ROLE_TIME; ridx = 0; break;
+        case 1: role = ROLE_CONS; ridx = 0; break;
+        case 5: role = ROLE_CONS; ridx = 1; break;
+        case 9: role = ROLE_CONS; ridx = 2; break;
+        case 3: role = ROLE_CONS; ridx = 3; break;
+        case 2: role = ROLE_EST; ridx = 0; break;
+        case 6: role = ROLE_EST; ridx = 1; break;
+        case 10: role = ROLE_EST; ridx = 2; break;
+        case 7: role = ROLE_EST; ridx = 3; break;
+        default: role = ROLE_EST; ridx = 4; break;     /* rw == 11 */
+    }
     unsigned char *outb = (unsigned char *)p.out + (long long)c * p.out_stride * (p.soft ? 4 : 1);
 
-    if (rw == 0) {
+    if (role == ROLE_OSC) {
         /* =========================== OSC ======================================================== */
         float2 ph = lane < M ? s_phi0[lane] : make_float2(1.0f, 0.0f);
         float2 *myring = ring + (lane < M ? lane : 0) * PIPE_R;
         int pos = 0;
+        PDECL
         for (int k = 0;; ++k) {
-            if (!warp_wait_ge(&s_est_done, k + 1, &s_stop, lane)) break;
+            { PTIC const bool ok_ = warp_wait_ge(&s_est_done, k + 1, &s_stop, lane); PTOC(0); if (!ok_) break; }
             const float2 d = desc[k & 3].dphi[lane < M ? lane : 0];
             int done = 0, target = nin_min, nin = -1;
             bool stopped = false;
@@ -151,18 +188,28 @@ __global__ void __launch_bounds__(FSK_THREADS) fsk_demod_pipe_kernel(const FskKP
                 while (done < target) {
                     const int n = min(PIPE_BLK - (pos & (PIPE_BLK - 1)), target - done);
                     int ok = 1;
+                    PTIC
                     if (lane == 0) {                                     /* ring space: slot of pos+n-1 must be free */
-                        while (pos + n - ld_acq(&s_free_pos) > PIPE_R) { if (ld_acq(&s_stop)) { ok = 0; break; } __nanosleep(40); }
+                        while (pos + n - ld_acq(&s_free_pos) > PIPE_R) { if (ld_acq(&s_stop)) { ok = 0; break; } __nanosleep(100); }
                     }
                     ok = __shfl_sync(0xffffffffu, ok, 0);
+                    PTOC(1);
                     if (!ok) { stopped = true; break; }
-                    if (lane < M) ph = osc_chunk(ph, d, myring + (pos & (PIPE_R - 1)), pos, n);
+                    if (lane < M) {
+                        float2 *dst = myring + (pos & (PIPE_R - 1));
+                        int j = 0;
+                        if (pos & 1) { ph = cmul_rn(ph, d); dst[0] = ph; j = 1; }          /* align to a 16-byte pair */
+                        const int npair = (n - j) & ~1;
+                        ph = osc_pairs(ph, d, dst + j, npair);
+                        j += npair;
+                        if (j < n) { ph = cmul_rn(ph, d); dst[j] = ph; }
+                    }
                     __syncwarp();
                     pos += n; done += n;
                     if (lane == 0) st_rel(&s_osc_pos, pos);
                 }
                 if (stopped || nin >= 0) break;
-                if (!warp_wait_ge(&s_published, k + 1, &s_stop, lane)) { stopped = true; break; }
+                { PTIC const bool ok_ = warp_wait_ge(&s_published, k + 1, &s_stop, lane); PTOC(2); if (!ok_) { stopped = true; break; } }
                 nin = desc[k & 3].nin; target = nin;
             }
             if (stopped) break;
@@ -173,28 +220,40 @@ __global__ void __launch_bounds__(FSK_THREADS) fsk_demod_pipe_kernel(const FskKP
             }
             __syncwarp();
         }
-    } else if (rw == 4) {
-        /* =========================== CTRL: timing, publish, decide ================================= */
+        PFLUSH(0, 3);
+    } else if (role == ROLE_TIME) {
+        /* =========================== TIME: fine timing, publish next frame ========================== */
         float nrt_state = s_nrt_state, ppm = s_ppm_state;
         int k = 0;
         bool exists = ld_acq(&s_published) >= 1;
+        PDECL
         while (exists) {
             const int ck = desc[k & 3].c, nin = desc[k & 3].nin;
+            const float2 *fint = fintb + (size_t)(k & 1) * M * nfi;
             float acc = 0.0f;
-            for (int i0 = 0; i0 < nfi; i0 += 32) {                       /* fsk.c:686-698, streamed */
-                const int cnt = min(32, nfi - i0);
-                warp_wait_ge(&s_fint_total, k * nfi + i0 + cnt, &s_stop, lane);
+            float2 pf0 = __ldg(p.phi_ft + min(lane, nfi - 1)), pf1 = __ldg(p.phi_ft + min(lane + 32, nfi - 1));
+            for (int i0 = 0; i0 < nfi; i0 += PIPE_TB) {                  /* fsk.c:686-698, streamed */
+                const int cnt = min(PIPE_TB, nfi - i0);
+                { PTIC warp_wait_ge(&s_fint_total, k * nfi + i0 + cnt, &s_stop, lane, 100); PTOC(0); }
+                const float2 q0 = pf0, q1 = pf1;
+                if (i0 + PIPE_TB < nfi) {                                /* prefetch the next batch's table entries */
+                    pf0 = __ldg(p.phi_ft + min(i0 + PIPE_TB + lane, nfi - 1));
+                    pf1 = __ldg(p.phi_ft + min(i0 + PIPE_TB + lane + 32, nfi - 1));
+                }
                 if (lane < cnt) {
-                    const int i = i0 + lane;
                     float ft1 = 0.0f;
-                    for (int m = 0; m < M; ++m) ft1 = __fadd_rn(ft1, mag2_rn(fint[m * nfi + i]));
-                    const float2 pf = __ldg(p.phi_ft + i);
-                    tbuf[lane] = make_float2(__fmul_rn(ft1, pf.x), __fmul_rn(ft1, pf.y));
+                    for (int m = 0; m < M; ++m) ft1 = __fadd_rn(ft1, mag2_rn(fint[m * nfi + i0 + lane]));
+                    tbuf[lane] = make_float2(__fmul_rn(ft1, q0.x), __fmul_rn(ft1, q0.y));
+                }
+                if (lane + 32 < cnt) {
+                    float ft1 = 0.0f;
+                    for (int m = 0; m < M; ++m) ft1 = __fadd_rn(ft1, mag2_rn(fint[m * nfi + i0 + lane + 32]));
+                    tbuf[lane + 32] = make_float2(__fmul_rn(ft1, q1.x), __fmul_rn(ft1, q1.y));
                 }
                 __syncwarp();
                 if (lane < 2) {
                     const float *t = (const float *)tbuf + lane;
-#pragma unroll 8
+#pragma unroll 16
                     for (int j = 0; j < cnt; ++j) acc = __fadd_rn(acc, t[2 * j]);
                 }
                 __syncwarp();
@@ -222,10 +281,25 @@ __global__ void __launch_bounds__(FSK_THREADS) fsk_demod_pipe_kernel(const FskKP
             if (lane == 0) {
                 s_nin_state = nin_next; s_nrt_state = nrt_state; s_ppm_state = ppm; s_high_last = high; s_nan_last = nan;
                 if (exists_next) { desc[(k + 1) & 3].nin = nin_next; desc[(k + 2) & 3].c = c_next + nin_next; st_rel(&s_published, k + 2); }
+                PipeDesc &dk = desc[k & 3];
+                dk.nan = nan; dk.low = low; dk.high = high; dk.nin_next = nin_next; dk.exists_next = exists_next ? 1 : 0;
+                dk.fract = fract; dk.nrt = nrt_state; dk.ppm = ppm;
+                st_rel(&s_time_done, k + 1);
             }
-            /* decisions (fsk.c:751-817) */
+            __syncwarp();
+            exists = exists_next; ++k;
+        }
+        PFLUSH(7, 1);
+    } else if (role == ROLE_DEC) {
+        /* =========================== DEC: decisions, outputs, EbNo sums, frame record ================ */
+        for (int k = 0;; ++k) {
+            if (!warp_wait_ge(&s_time_done, k + 1, &s_stop, lane)) break;
+            const PipeDesc &dk = desc[k & 3];
+            const int nan = dk.nan, low = dk.low, high = dk.high, nin = dk.nin, exists_next = dk.exists_next;
+            const float fract = dk.fract;
+            const float2 *fint = fintb + (size_t)(k & 1) * M * nfi;
             const long long ofs = (long long)(fbase + k) * p.Nbits;
-            if (!nan) {
+            if (!nan) {                                                  /* fsk.c:751-817 */
                 const float omf = __fsub_rn(1.0f, fract);
                 for (int i = lane; i < nsym; i += 32) {
                     const int st = (i + 1) * P;
@@ -255,7 +329,7 @@ __global__ void __launch_bounds__(FSK_THREADS) fsk_demod_pipe_kernel(const FskKP
                         }
                     }
                 }
-            } else {
+            } else {                                                     /* stale frame, fsk_demod.c:424-433 */
                 for (int i = lane; i < p.Nbits; i += 32) {
                     if (p.soft) {
                         float *o = (float *)outb;
@@ -267,20 +341,19 @@ __global__ void __launch_bounds__(FSK_THREADS) fsk_demod_pipe_kernel(const FskKP
                 }
             }
             __syncwarp();
-            /* EbNo sums (fsk.c:808-815): sequential, lanes 0 (sum of max) and 1 (sum of sqrt(max)) */
-            float es = 0.0f;
+            float es = 0.0f;                                             /* EbNo sums (fsk.c:808-815), sequential */
             if (lane < 2 && !nan) {
                 const float *t = (const float *)s_maxs + lane;
-#pragma unroll 4
+#pragma unroll 8
                 for (int i = 0; i < nsym; ++i) es = __fadd_rn(es, t[2 * i]);
             }
             const float mean_sum = __shfl_sync(0xffffffffu, es, 1);
             if (lane == 0) {
                 if (p.write_recs) {
                     FskFrameRec r;
-                    r.nin_used = nin; r.nin_next = nin_next; r.norm_rx_timing = nrt_state; r.ppm = ppm;
+                    r.nin_used = nin; r.nin_next = dk.nin_next; r.norm_rx_timing = dk.nrt; r.ppm = dk.ppm;
                     r.mean_sum = mean_sum; r.std_sum = es; r.nanflag = nan; r.high_sample = high;
-                    for (int m = 0; m < 4; ++m) r.tabidx[m] = m < M ? desc[k & 3].tabidx[m] : 0;
+                    for (int m = 0; m < 4; ++m) r.tabidx[m] = m < M ? dk.tabidx[m] : 0;
                     p.recs[(long long)c * p.rec_stride + fbase + k] = r;
                 }
                 s_frames = k + 1;
@@ -289,25 +362,24 @@ __global__ void __launch_bounds__(FSK_THREADS) fsk_demod_pipe_kernel(const FskKP
                 if (!exists_next) st_rel(&s_stop, 1);
             }
             __syncwarp();
-            exists = exists_next; ++k;
+            if (!exists_next) break;
         }
-    } else if (rw >= 6) {
+    } else if (role == ROLE_CONS) {
         /* =========================== CONS: down-convert + integrate, streaming ===================== */
-        const int ct = (rw - 6) * 32 + lane, NCT = PIPE_NCONS * 32;
+        const int ct = ridx * 32 + lane, NCT = PIPE_NCONS * 32;
+        PDECL
         for (int k = 0;; ++k) {
-            if (!warp_wait_ge(&s_published, k + 1, &s_stop, lane)) break;
-            if (!warp_wait_ge(&s_decide_done, k, &s_stop, lane)) break;
+            { PTIC const bool ok_ = warp_wait_ge(&s_published, k + 1, &s_stop, lane) && warp_wait_ge(&s_decide_done, k - 1, &s_stop, lane); PTOC(0); if (!ok_) break; }
             const int ck = desc[k & 3].c, nin = desc[k & 3].nin, base = ck + nin - Nmem, fend = ck + nin;
-            int i_done = 0; bool stopped = false;
+            float2 *fint = fintb + (size_t)(k & 1) * M * nfi;
+            int i_done = 0;
+            float2 xn = make_float2(0.0f, 0.0f);
+            if (ct < min(PIPE_BLK, fend - ck)) xn = load_sample_t<FMT>(p.in, gbase + ck + ct);
             for (int s0 = ck; s0 < fend; s0 += PIPE_BLK) {
                 const int cnt = min(PIPE_BLK, fend - s0);
-                float2 xv = make_float2(0.0f, 0.0f);
-                if (ct < cnt) xv = load_sample(p.in, p.fmt, gbase + s0 + ct);
-                if (!warp_wait_ge(&s_osc_pos, s0 + cnt, &s_stop, lane)) { stopped = true; }
-                /* both CONS warps must take the same exit: agree through the group barrier below only if not stopped.
-                   s_stop is raised only after the last existing frame is fully consumed, so a stop seen here means
-                   this frame does not exist -- cannot happen for a published frame; kept for safety. */
-                if (stopped) break;
+                const float2 xv = xn;
+                if (s0 + PIPE_BLK + ct < fend) xn = load_sample_t<FMT>(p.in, gbase + s0 + PIPE_BLK + ct);   /* prefetch next block */
+                { PTIC warp_wait_ge(&s_osc_pos, s0 + cnt, &s_stop, lane, 100); PTOC(1); }   /* a published frame is always completed by OSC */
                 if (ct < cnt) {
                     const int slot = (s0 + ct) & (PIPE_R - 1);
                     for (int m = 0; m < M; ++m) {
@@ -320,8 +392,8 @@ __global__ void __launch_bounds__(FSK_THREADS) fsk_demod_pipe_kernel(const FskKP
                 int i_hi = 0;
                 if (mixed_end - base >= Ts) i_hi = min(nfi, (mixed_end - base - Ts) / step + 1);
                 const int ni = i_hi - i_done;
-                for (int e = ct; e < M * ni; e += NCT) {                 /* fsk.c:660-668 */
-                    const int m = e / ni, i = i_done + (e - m * ni);
+                for (int e = ct; e < (ni << lgM); e += NCT) {            /* fsk.c:660-668 */
+                    const int m = e & (M - 1), i = i_done + (e >> lgM);
                     const float2 *rg = ring + m * PIPE_R;
                     const int a0 = base + i * step;
                     float2 acc = make_float2(0.0f, 0.0f);
@@ -335,45 +407,61 @@ __global__ void __launch_bounds__(FSK_THREADS) fsk_demod_pipe_kernel(const FskKP
                 }
                 i_done = i_hi;
             }
-            if (stopped) break;
         }
+        if (ridx == 0) PFLUSH(4, 2);
     } else {
         /* =========================== EST: FFTs -> Sf -> tone estimate, one frame ahead =============== */
-        const int ew = (rw <= 3) ? rw - 1 : 3;                           /* rw in {1,2,3,5} -> 0..3 */
+        const int ew = ridx;
         const int et = ew * 32 + lane, NET = PIPE_NEST * 32;
         const int numffts = (int)floorf(__fdiv_rn((float)nin_min, (float)(Ndft / 2))) - 1;   /* same for all 3 nin (host-checked) */
-        float2 *F = fftbuf + ew * Ndft;
+        float2 *F = fftbuf + ew * (Ndft + (Ndft >> 3));                  /* padded: i -> i + i/8 */
+        const int npl = (Ndft + 31) >> 5;                                /* samples per lane per window (<= 8: Ndft <= 256) */
+        PDECL
         for (int k = 0;; ++k) {
-            if (!warp_wait_ge(&s_published, k, &s_stop, lane)) break;
+            { PTIC const bool ok_ = warp_wait_ge(&s_published, k, &s_stop, lane); PTOC(0); if (!ok_) break; }
             const int ck = desc[k & 3].c;
             if (!(ck + nin_min <= nsamp_rel && (p.max_frames <= 0 || k < p.max_frames))) break;   /* frame k cannot exist */
             const float *Sf_in = Sfbuf + ((k + 1) & 1) * Ndft;
             float *Sf_out = Sfbuf + (k & 1) * Ndft;
-            if (numffts <= 0) { for (int i = et; i < Ndft; i += NET) Sf_out[i] = Sf_in[i]; group_bar(1, NET); }
-            for (int r0 = 0; r0 < numffts; r0 += PIPE_NEST) {
-                const int j = r0 + ew;
-                if (j < numffts) {
-                    const long long a = gbase + ck + j * (Ndft / 2);
-                    for (int i = lane; i < Ndft; i += 32) {              /* fsk.c:470-478, coalesced read, scatter to DIT order */
-                        const float2 v = load_sample(p.in, p.fmt, a + i);
-                        const float h = s_hann[i];
-                        F[s_iperm[i]] = make_float2(__fmul_rn(h, v.x), __fmul_rn(h, v.y));
-                    }
-                    __syncwarp();
-                    warp_fft(F, s_tw, p, lane);
-                    for (int i = lane; i < Ndft; i += 32) magbuf[ew * Ndft + i] = __fsqrt_rn(mag2_rn(F[i]));
-                }
-                group_bar(1, NET);
-                const int cnt = min(PIPE_NEST, numffts - r0);
-                for (int i = et; i < Ndft; i += NET) {
-                    float s = (r0 == 0) ? Sf_in[i] : Sf_out[i];
-                    const int src = (i + Ndft / 2) & (Ndft - 1);
-                    for (int jj = 0; jj < cnt; ++jj)
-                        s = __fadd_rn(__fmul_rn(s, p.omtc), __fmul_rn(magbuf[jj * Ndft + src], p.tc));    /* fsk.c:500 */
-                    Sf_out[i] = s;
-                }
-                group_bar(1, NET);
+            /* this warp's windows: j = ew, ew+NEST, ...; the next window's samples are fetched while the current FFT runs */
+            float2 v[8];
+            { PTIC
+            if (ew < numffts) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { const int i = q * 32 + lane; if (q < npl && i < Ndft) v[q] = load_sample_t<FMT>(p.in, gbase + ck + ew * (Ndft / 2) + i); }
             }
+            PTOC(1); }
+            for (int j = ew; j < numffts; j += PIPE_NEST) {
+                { PTIC
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {                            /* fsk.c:470-478: window, scatter to DIT order */
+                    const int i = q * 32 + lane;
+                    if (q < npl && i < Ndft) { const float h = s_hann[i]; F[fpad<true>(s_iperm[i])] = make_float2(__fmul_rn(h, v[q].x), __fmul_rn(h, v[q].y)); }
+                }
+                if (j + PIPE_NEST < numffts) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) { const int i = q * 32 + lane; if (q < npl && i < Ndft) v[q] = load_sample_t<FMT>(p.in, gbase + ck + (j + PIPE_NEST) * (Ndft / 2) + i); }
+                }
+                __syncwarp();
+                PTOC(1); }
+                { PTIC
+                warp_fft<true>(F, s_tw, p, lane);
+                for (int i = lane; i < Ndft; i += 32) magbuf[j * Ndft + i] = __fsqrt_rn(mag2_rn(F[fpad<true>(i)]));
+                __syncwarp();
+                PTOC(2); }
+            }
+            { PTIC
+            group_bar(1, NET);
+            for (int i = et; i < Ndft; i += NET) {                       /* Sf IIR over the frame's FFTs, in order (fsk.c:500) */
+                float s = Sf_in[i];
+                const int src = (i + Ndft / 2) & (Ndft - 1);
+#pragma unroll 4
+                for (int jj = 0; jj < numffts; ++jj)
+                    s = __fadd_rn(__fmul_rn(s, p.omtc), __fmul_rn(magbuf[jj * Ndft + src], p.tc));
+                Sf_out[i] = s;
+            }
+            group_bar(1, NET);
+            PTOC(3); }
             if (ew == 0) {
                 int tabidx[4];
                 estimate_tones(p, Sf_out, scr, s_mask, lane, tabidx);
@@ -382,6 +470,7 @@ __global__ void __launch_bounds__(FSK_THREADS) fsk_demod_pipe_kernel(const FskKP
                 if (lane == 0) st_rel(&s_est_done, k + 1);
             }
         }
+        if (ew == 0) PFLUSH(11, 4);
     }
     __syncthreads();
 
@@ -389,8 +478,9 @@ __global__ void __launch_bounds__(FSK_THREADS) fsk_demod_pipe_kernel(const FskKP
     const int frames = s_frames;
     const int c_end = frames > 0 ? desc[frames & 3].c : 0;             /* desc[k+1].c is written when frame k is published */
     const float *Sf_fin = Sfbuf + ((frames + 1) & 1) * Ndft;            /* buffer (frames-1)&1 */
-    for (int i = tid; i < Ndft; i += FSK_THREADS) p.Sf[(long long)c * Ndft + i] = Sf_fin[i];
-    for (int e = tid; e < M * p.tailcap; e += FSK_THREADS) {
+    const float2 *fint = fintb + (size_t)((frames + 1) & 1) * M * nfi;  /* f_int of the last frame */
+    for (int i = tid; i < Ndft; i += PIPE_THREADS) p.Sf[(long long)c * Ndft + i] = Sf_fin[i];
+    for (int e = tid; e < M * p.tailcap; e += PIPE_THREADS) {
         const int m = e / p.tailcap, i = e - m * p.tailcap;
         p.fdc_tail[((long long)c * M + m) * p.tailcap + i] = ring[m * PIPE_R + ((c_end - p.tailcap + i) & (PIPE_R - 1))];
     }
@@ -403,11 +493,11 @@ __global__ void __launch_bounds__(FSK_THREADS) fsk_demod_pipe_kernel(const FskKP
     }
     if (frames > 0) {
         const long long ofs = (long long)(fbase + frames - 1) * p.Nbits;
-        for (int i = tid; i < p.Nbits; i += FSK_THREADS)
+        for (int i = tid; i < p.Nbits; i += PIPE_THREADS)
             p.last_out[(long long)c * p.Nbits + i] = p.soft ? __float_as_uint(((const float *)outb)[ofs + i]) : (unsigned int)outb[ofs + i];
         if (p.write_recs && !s_nan_last) {
             const int neyeoffset = s_high_last + 1, tot = p.eye_traces * M * p.neyesamp;
-            for (int e = tid; e < tot; e += FSK_THREADS) {
+            for (int e = tid; e < tot; e += PIPE_THREADS) {
                 const int row = e / p.neyesamp, j = e - row * p.neyesamp, i = row / M, m = row - i * M;
                 const int ind = 2 * P * i + neyeoffset + j * p.eye_dec, flat = m * nfi + ind;
                 float2 v = make_float2(0.0f, 0.0f);
@@ -418,9 +508,10 @@ __global__ void __launch_bounds__(FSK_THREADS) fsk_demod_pipe_kernel(const FskKP
     }
     if (p.carry_cap > 0) {                                             /* same tail carry as the serial kernel */
         const long long cursor = start + c_end, tail = p.nsamp - cursor;
-        const int es = p.fmt == 1 ? 8 : (p.fmt == 0 ? 4 : 2);
+        constexpr int es = FMT == 1 ? 8 : (FMT == 0 ? 4 : 2);
         const long long nhalf = tail * es / 2;
         const int chunk = (int)(p.q_stage_bytes / 2);
+        __syncthreads();
         unsigned short *stage = (unsigned short *)(smem + p.q_fint);    /* f_int is dead now (eye already written) */
         const long long base = (long long)c * p.in_stride;
         const unsigned short *src = (const unsigned short *)((const unsigned char *)p.in + (base + cursor) * es);
@@ -428,9 +519,9 @@ __global__ void __launch_bounds__(FSK_THREADS) fsk_demod_pipe_kernel(const FskKP
         for (long long k0 = 0; k0 < nhalf; k0 += chunk) {
             const int n = (int)min((long long)chunk, nhalf - k0);
             __syncthreads();
-            for (int i = tid; i < n; i += FSK_THREADS) stage[i] = src[k0 + i];
+            for (int i = tid; i < n; i += PIPE_THREADS) stage[i] = src[k0 + i];
             __syncthreads();
-            for (int i = tid; i < n; i += FSK_THREADS) dst[k0 + i] = stage[i];
+            for (int i = tid; i < n; i += PIPE_THREADS) dst[k0 + i] = stage[i];
         }
         if (tid == 0) p.in_off_next[c] = (int)(p.carry_cap - tail);
     }
