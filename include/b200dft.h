@@ -1,0 +1,86 @@
+/* b200dft.h -- C-ABI of the B200-native batched sonde-type detector (dft_detect).
+ *
+ * Drop-in boundary for scan/dft_detect.c in its production IQ mode
+ *     dft_detect [-v] [-c] [-t sec] --iq --bw <kHz> [--dc] - <sample_rate> <8|16|32>
+ * (auto_rx/autorx/scan.py:541-547, scan_async.py:143-148).  The reference is a stdin->stdout executable with
+ * all state in file-scope statics; there is no in-process API, so the entry points below are what a binding
+ * replacing "one dft_detect process per candidate frequency" (scan.py:621, scan_async.py:209-222) would call:
+ *
+ *   reference (file:line)                                        here
+ *   ----------------------------------------------------------   -------------------------------------
+ *   argv parsing + init_buffers          dft_detect.c:1368-1476   b200dft_create (sample_rate, bw, dc)
+ *   while(f32buf_sample) ... getCorrDFT  dft_detect.c:1492-1512   b200dft_run_host / b200dft_run_device
+ *   threshold/headcmp/M10/iMet + printf  dft_detect.c:1514-1652   result records (type, score, pos, df)
+ *   exit code  header_found * tn         dft_detect.c:1660-1666   b200dft_result_t.exit_code
+ *
+ * One handle = nchan independent IQ streams (one per candidate frequency), processed concurrently.
+ * Detected type, sign and sample position are identical to the reference's; scores agree to ~1e-4 (the
+ * reference itself is built -Ofast, so its float sums are not reproducible bit for bit).
+ * Plain pointers and sizes only.  No CPU fallback: without a CUDA device b200dft_create fails.
+ */
+#ifndef B200DFT_H
+#define B200DFT_H
+#include <stdint.h>
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200DFT_OK       0
+#define B200DFT_EINVAL  -1
+#define B200DFT_ECUDA   -2
+#define B200DFT_ERANGE  -4
+
+#define B200DFT_FMT_CS16 0    /* int16 I,Q  /32768   (dft_detect.c:567-571) */
+#define B200DFT_FMT_F32  1    /* float I,Q           (dft_detect.c:561-565) */
+#define B200DFT_FMT_CU8  2    /* uint8 I,Q  (u-128)/128 (dft_detect.c:573-577) */
+
+#define B200DFT_NHDR 18       /* rows of rs_hdr[] (dft_detect.c:177-194) */
+#define B200DFT_MAXDET 16     /* detections kept per channel */
+
+typedef struct b200dft b200dft_t;
+
+typedef struct {              /* one line the reference prints (dft_detect.c:1620-1634) */
+    int      hdr;             /* row of the header bank                                 */
+    int      tn;              /* type number (dft_detect.c:152-170)                     */
+    float    score;           /* signed normalised correlation, "%.4f"                  */
+    uint32_t pos;             /* "sample: N" (-v)                                       */
+    float    df_hz;           /* " , %+.1fHz" (--dc --iq)                               */
+    uint32_t m10;             /* M10/M20 frame bytes (-v "[%04X]")                      */
+    char     type[12];        /* "RS41", "DFM9", "M20", ...                             */
+} b200dft_det_t;
+
+typedef struct {
+    int exit_code;            /* what the process would return: +-tn of the best score, 0 = nothing */
+    int ndet;                 /* lines printed (capped at B200DFT_MAXDET in dets[])                  */
+    b200dft_det_t dets[B200DFT_MAXDET];
+} b200dft_result_t;
+
+typedef struct {
+    int sample_rate, N_DFT, K, L, M, delay, lpIQtaps, lpFMtaps, nhdr_active, nchan;
+} b200dft_info_t;
+
+/* bw_khz is the --bw argument (required: the CUDA path implements the single-IF-filter mode that --bw selects,
+ * dft_detect.c:1132-1137, which is what auto_rx always passes); opt_dc is --dc. */
+int  b200dft_create(b200dft_t **out, int sample_rate, double bw_khz, int opt_dc, int nchan, int device);
+void b200dft_destroy(b200dft_t *h);
+int  b200dft_info(const b200dft_t *h, b200dft_info_t *info);
+const char *b200dft_last_error(void);
+
+/* Whole detector run over nchan in-memory streams of nsamp samples each (channel stride in_stride samples).
+ * opt_cont = -c (keep going after a detection); tl = -t seconds (<=0: none).  res[nchan] receives what each
+ * reference process would have printed and returned. Host buffers: H2D inside the call. */
+int  b200dft_run_host(b200dft_t *h, const void *h_iq, int fmt, long in_stride, long nsamp, int opt_cont, double tl,
+                      b200dft_result_t *res);
+/* Same with the IQ already on the device. */
+int  b200dft_run_device(b200dft_t *h, const void *d_iq, int fmt, long in_stride, long nsamp, int opt_cont, double tl,
+                        b200dft_result_t *res);
+
+long  b200dft_launch_count(const b200dft_t *h);
+/* device time (ms) of the front-end kernels and of the correlator kernel in the most recent run */
+int   b200dft_last_kernel_ms(b200dft_t *h, float *front_ms, float *corr_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

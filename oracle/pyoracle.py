@@ -252,3 +252,60 @@ def ref_cli_fsk_demod(cfg: FskConfig, raw: bytes, fmt: str = "cs16", extra: list
     args = [exe] + (extra or []) + cfg.cli_args(fmt) + ["-", "-"]
     r = subprocess.run(args, input=raw, capture_output=True)
     return r.stdout, r.stderr, r.returncode
+
+
+# ------------------------------------------------------------------------------------------------
+# dft_detect: our restatement (liboracle.so) and the reference binary (oracle/_ref/dft_detect)
+# ------------------------------------------------------------------------------------------------
+class DftDet(C.Structure):
+    _fields_ = [("hdr", C.c_int), ("tn", C.c_int), ("score", C.c_float), ("pos", C.c_uint), ("df_hz", C.c_float),
+                ("m10", C.c_uint), ("type", C.c_char * 12)]
+
+
+class DftBlk(C.Structure):
+    _fields_ = [("hdr", C.c_int), ("mp", C.c_int), ("score", C.c_float), ("pos", C.c_uint), ("dc", C.c_float),
+                ("sample_in", C.c_uint)]
+
+
+def dft_oracle_run(iq: np.ndarray, sample_rate: int = 48000, bw_khz: float = 15.0, dc: bool = True, cont: bool = True,
+                   tl: float = -1.0, want_blocks: bool = False):
+    """-> (exit_code, [(type, score, pos, df_hz)], blocks or None)"""
+    L = lib()
+    L.dfto_run.restype = C.c_int
+    L.dfto_run.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double,
+                           C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    iq = np.ascontiguousarray(iq)
+    bits = {np.dtype(np.int16): 16, np.dtype(np.float32): 32, np.dtype(np.uint8): 8}[iq.dtype]
+    nsamp = iq.size // 2
+    dets = (DftDet * 4096)()
+    nd, nb = C.c_int(0), C.c_int(0)
+    maxb = (nsamp // 5000 + 2) * 16 if want_blocks else 0
+    blks = (DftBlk * max(maxb, 1))()
+    rc = L.dfto_run(iq.ctypes.data, nsamp, bits, sample_rate, bw_khz, int(dc), int(cont), tl, dets, 4096, C.byref(nd),
+                    blks if want_blocks else None, maxb, C.byref(nb))
+    out = [(dets[i].type.decode(), dets[i].score, dets[i].pos, dets[i].df_hz) for i in range(min(nd.value, 4096))]
+    bl = [(b.hdr, b.mp, b.score, b.pos, b.dc, b.sample_in) for b in blks[: nb.value]] if want_blocks else None
+    return rc, out, bl
+
+
+def ref_cli_dft_detect(iq: np.ndarray, sample_rate: int = 48000, bw_khz: float = 15.0, dc: bool = True, cont: bool = True,
+                       tl: float | None = None, bits: int = 16):
+    """Run oracle/_ref/dft_detect -v on stdin bytes -> (exit_code as signed int8-ish, [(type, score, pos, df_hz)])."""
+    exe = os.path.join(REF_DIR, "dft_detect")
+    if not os.path.exists(exe):
+        build()
+    args = [exe, "-v"] + (["-c"] if cont else []) + (["-t", str(tl)] if tl is not None else []) + ["--iq", "--bw", str(bw_khz)]
+    args += (["--dc"] if dc else []) + ["-", str(sample_rate), str(bits)]
+    r = subprocess.run(args, input=np.ascontiguousarray(iq).tobytes(), capture_output=True)
+    import re
+    dets, pos = [], None
+    for ln in r.stdout.decode().splitlines():
+        if ln.startswith("sample:"):
+            pos = int(ln.split(":")[1])
+            continue
+        m = re.match(r"^(\w+): (-?[0-9.]+)", ln)
+        if m:
+            mh = re.search(r", ([+-][0-9.]+)Hz", ln)
+            dets.append((m.group(1), float(m.group(2)), pos, float(mh.group(1)) if mh else 0.0))
+    rc = r.returncode if r.returncode < 128 else r.returncode - 256
+    return rc, dets

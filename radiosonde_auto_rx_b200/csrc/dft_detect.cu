@@ -1,0 +1,588 @@
+/* dft_detect.cu -- libb200dft.so: batched sonde-type detector on B200 (C-ABI of include/b200dft.h).
+ *
+ * Reference: scan/dft_detect.c (production IQ mode, `--iq --bw B --dc`).  The reference runs, per candidate
+ * frequency, one single-threaded process that (a) removes the IQ DC, low-pass filters the IF, FM-demodulates
+ * (dft_detect.c:556-591, 709-716, 780-811) and (b) every K-4 samples cross-correlates the last K+L_j FM
+ * samples with 14 matched header templates through three 8192-point FFTs per header (getCorrDFT, :357-443,
+ * 93 % of its CPU time), then (c) applies thresholds / header bit checks (:1514-1652).
+ *
+ * Here the batch of channels is processed by three kernels:
+ *   dft_dcavg_kernel   block means of the raw IQ (the DC estimate the reference refreshes every sr/32 samples)
+ *   dft_front_kernel   fused  int16->float, DC subtraction, 49-tap IF FIR, FM discriminator x2  -> two FM streams
+ *                      in HBM (filtered: rings 0-2 of the reference; unfiltered: ring 3)
+ *   dft_corr_kernel    one CTA per (channel, block, header): window -> DC estimate -> 97-tap FM low-pass ->
+ *                      DIRECT time-domain matched-filter correlation with register-tiled sliding dot products
+ *                      (the FFTs of the reference are replaced outright: same circular-convolution definition,
+ *                      evaluated exactly, FP32 FMA) -> peak (first maximum of corr^2), normalisation, and, for
+ *                      threshold crossings, the header bit re-slice (headcmp) and the M10/M20 frame bytes.
+ * The per-channel decision loop of main() (mv_pos ordering, -c, exit code) runs on the host over the tiny
+ * per-block result records.  No CPU fallback exists for the DSP.
+ */
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include <string>
+#include "../../include/b200dft.h"
+
+#define NRS 18
+#define IDX_IMETAFSK 15
+#define IDX_RS 16
+#define IDX_I4 17
+#define SKIP_A 11                /* C34C50:  -DNOC34C50  (scan/Makefile:1)  */
+#define SKIP_B 14                /* IMET1AB: -DNOIMET1AB (scan/Makefile:1)  */
+#define FM_GAIN 0.8
+#define CORR_THREADS 256
+#define CORR_R 8                 /* lags per thread (register tile) */
+#define FRONT_TILE 512
+
+static thread_local std::string g_err;
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[512]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf; return code;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(B200DFT_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
+extern "C" const char *b200dft_last_error(void) { return g_err.c_str(); }
+
+struct HdrDef { int sps; const char *header; float BT, thres; int herrs; const char *type; int tn, lpFM, lpIQ; };
+/* the header bank: strings scan/dft_detect.c:43-126, table :177-194 */
+static const HdrDef HDR[NRS] = {
+    {2500, "10011010100110010101101001010101", 1.0f, 0.65f, 2, "DFM9", 2, 0, 1},
+    {4800, "0000100001101101010100111000100001000100011010010100100000011111", 0.5f, 0.70f, 2, "RS41", 3, 0, 1},
+    {4800, "10100110011001101001" "10100110011001101001" "1010011001100110100110101010100110101001", 0.5f, 0.70f, 3, "RS92", 4, 0, 1},
+    {4800, "0101011000001000" "0001110010010111" "0001101010100111" "0011110100111110", 1.0f, 0.60f, 8, "LMS6", 8, 0, 1},
+    {4800, "0000000001" "0101010101" "0001001001" "0001001001", 0.5f, 0.80f, 2, "IMET5", 24, 0, 1},
+    {9616, "0010100111" "0010100111" "0001001001" "0010010101", 1.0f, 0.70f, 2, "MK2LMS", 18, 1, 2},
+    {9608, "1001100110010100110010011001" "1010", 1.0f, 0.76f, 2, "M10", 5, 1, 2},
+    {2400, "110011001101001101001101010100101010110010101010", 1.0f, 0.70f, 2, "MEISEI", 9, 0, 2},
+    {4800, "10100110010110101001" "10010101011010010101" "10101001010101010101" "10011001010110101001", 1.0f, 0.70f, 2, "RD94RD41", 10, 0, 1},
+    {2400, "1001100110011001" "1001101010101010", 1.5f, 0.80f, 2, "MRZ", 12, 0, 1},
+    {1200, "10101010" "10101010" "10110100" "00101011", 1.0f, 0.65f, 2, "MTS01", 13, 0, 0},
+    {5800, "01010101010101010101010101010101", 1.5f, 0.80f, 2, "C34C50", 15, 0, 2},
+    {4800, "10101010" "10101010" "10101010" "00101101" "11010100", 1.0f, 0.65f, 2, "WXR301", 16, 0, 3},
+    {5000, "10101010" "10101010" "10101010" "11000001" "10010100", 1.0f, 0.65f, 2, "WXRPN9", 17, 0, 3},
+    {9600, "0000" "11110000111100001111000011110000" "1111" "0000" "10101100110010101100101010101100" "1111", 1.0f, 0.80f, 2, "IMET1AB", 29, 1, 3},
+    {9600, "11110000111100001111000011110000" "11110000111100001111000011110000", 0.5f, 0.80f, 4, "IMETafsk", 25, 1, 1},
+    {9600, "0000" "1111" "0000" "1111" "0000" "1111" "0000" "1111", 0.5f, 0.80f, 2, "IMET1RS", 28, 0, 3},
+    {9600, "0000" "1111" "0000" "1111" "0000" "1111" "0000" "1111", 0.5f, 0.80f, 2, "IMET4", 26, 1, 1},
+};
+
+struct BlkRes {                  /* getCorrDFT outputs of one (channel, block, header) + candidate check */
+    float score; unsigned pos; float dc; int mp; int herrs; unsigned m10;
+};
+
+struct HdrDev {                  /* per active header, device side */
+    int j, L, Lpad, hLen, use_raw, lpFM, match_off;     /* Lpad = L rounded up to 8; match_off into the match table */
+    float spb, thres;
+    unsigned char bits[96];     /* header bits 0/1 */
+};
+
+struct DftParams {
+    int nchan, nact, N, K, L, lpIQtaps, lpFMtaps, delay, opt_dc, maxcnt, nblk, navg;
+    long long nsamp, in_stride;
+    int fmt;
+    const void *iq;
+    const float *ws_lpIQ;        /* lpIQtaps */
+    const float *ws_lpFM;        /* [2][lpFMtaps] */
+    const float *match;          /* concatenated, each padded to a multiple of 8 with zeros */
+    const HdrDev *hdr;           /* nact */
+    float2 *avg;                 /* [nchan][navg] DC estimate valid for DC-block i */
+    float *fm_filt, *fm_raw;     /* [nchan][nsamp] */
+    BlkRes *res;                 /* [nchan][nblk][nact] */
+};
+
+/* raw sample -> float pair, the conversions of f32read_csample (dft_detect.c:561-578) */
+__device__ __forceinline__ float2 dft_load(const void *iq, int fmt, long long idx)
+{
+    if (fmt == 1) return __ldg((const float2 *)iq + idx);
+    if (fmt == 0) { const short2 s = __ldg((const short2 *)iq + idx); return make_float2((float)((double)s.x / 32768.0), (float)((double)s.y / 32768.0)); }
+    const uchar2 u = __ldg((const uchar2 *)iq + idx);
+    return make_float2((float)(((int)u.x - 128) / 128.0), (float)(((int)u.y - 128) / 128.0));
+}
+
+/* ---- K0: mean of every block of maxcnt raw samples (IQdc, dft_detect.c:583-588); avg[i+1] applies to block i+1 ---- */
+__global__ void dft_dcavg_kernel(const DftParams p)
+{
+    const int c = blockIdx.y, blk = blockIdx.x;
+    const long long s0 = (long long)blk * p.maxcnt;
+    double sx = 0.0, sy = 0.0;
+    for (int i = threadIdx.x; i < p.maxcnt; i += blockDim.x) {
+        const long long n = s0 + i;
+        if (n < p.nsamp) { const float2 v = dft_load(p.iq, p.fmt, (long long)c * p.in_stride + n); sx += v.x; sy += v.y; }
+    }
+    __shared__ double shx[4], shy[4];
+    for (int o = 16; o; o >>= 1) { sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o); }
+    if ((threadIdx.x & 31) == 0) { shx[threadIdx.x >> 5] = sx; shy[threadIdx.x >> 5] = sy; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        sx = shx[0] + shx[1] + shx[2] + shx[3]; sy = shy[0] + shy[1] + shy[2] + shy[3];
+        float2 a = make_float2((float)(sx / (double)(float)p.maxcnt), (float)(sy / (double)(float)p.maxcnt));
+        if (s0 + p.maxcnt > p.nsamp) a = make_float2(0.f, 0.f);            /* incomplete block: never becomes an estimate */
+        p.avg[(long long)c * p.navg + blk + 1] = a;
+        if (blk == 0) p.avg[(long long)c * p.navg] = make_float2(0.f, 0.f);
+    }
+}
+
+/* ---- K1: fused front end: DC subtraction -> IF FIR -> FM discriminator (filtered + unfiltered) ------------------ */
+__global__ void __launch_bounds__(FRONT_TILE) dft_front_kernel(const DftParams p)
+{
+    extern __shared__ float2 sm[];
+    const int taps = p.lpIQtaps;
+    float2 *z = sm;                                  /* [FRONT_TILE + taps]  : samples t0-taps .. t0+TILE-1 */
+    float2 *y = sm + FRONT_TILE + taps;              /* [FRONT_TILE + 1]     : filtered t0-1 .. t0+TILE-1    */
+    __shared__ float ws[256];
+    const int c = blockIdx.y;
+    const long long t0 = (long long)blockIdx.x * FRONT_TILE;
+    for (int i = threadIdx.x; i < taps; i += FRONT_TILE) ws[i] = p.ws_lpIQ[i];
+    for (int i = threadIdx.x; i < FRONT_TILE + taps; i += FRONT_TILE) {
+        const long long n = t0 - taps + i;
+        float2 v = make_float2(0.f, 0.f);
+        if (n >= 0 && n < p.nsamp) {
+            const float2 r = dft_load(p.iq, p.fmt, (long long)c * p.in_stride + n);
+            const float2 a = p.avg[(long long)c * p.navg + (int)(n / p.maxcnt)];
+            v = make_float2(r.x - a.x, r.y - a.y);                           /* dft_detect.c:581 */
+        }
+        z[i] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < FRONT_TILE + 1; i += FRONT_TILE) {          /* y[n] = sum_k ws[k] z[n-k]  (:709-716) */
+        float2 acc = make_float2(0.f, 0.f);
+        const float2 *zp = z + taps - 1 + i;                                 /* sample n = t0-1+i */
+#pragma unroll 7
+        for (int k = 0; k < taps; ++k) { const float w = ws[k]; const float2 v = zp[-k]; acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); }
+        y[i] = acc;
+    }
+    __syncthreads();
+    const long long n = t0 + threadIdx.x;
+    if (n < p.nsamp) {
+        const float g = (float)(FM_GAIN / M_PI);
+        const float2 a = y[threadIdx.x + 1], b = y[threadIdx.x];             /* w = z_fm * conj(z_fm_prev)  (:780-781) */
+        const float wr = a.x * b.x + a.y * b.y, wi = a.y * b.x - a.x * b.y;
+        p.fm_filt[(long long)c * p.nsamp + n] = g * atan2f(wi, wr);
+        const float2 a2 = z[taps + threadIdx.x], b2 = z[taps + threadIdx.x - 1];
+        const float vr = a2.x * b2.x + a2.y * b2.y, vi = a2.y * b2.x - a2.x * b2.y;
+        p.fm_raw[(long long)c * p.nsamp + n] = g * atan2f(vi, vr);            /* ring 3 (:798-800) */
+    }
+}
+
+/* ---- K2: matched-filter correlator, one CTA per (block, header, channel) ---------------------------------- */
+__device__ __forceinline__ int pad8(int i) { return i + (i >> 3); }   /* one float of padding per 8: stride-8 threads hit distinct banks */
+
+__device__ __forceinline__ float fm_at(const float *fm, long long n) { return n >= 0 ? __ldg(fm + n) : 0.0f; }
+
+/* read_bufbit (dft_detect.c:821-864): integrate-and-dump bit slicer on the un-low-passed FM stream */
+__device__ void slice_bits(const float *fm, long long mvp, float spb, float dc, int symlen, int nsym, unsigned &rcount, float &grenze,
+                           unsigned char *out)
+{
+    for (int b = 0; b < nsym; ++b) {
+        double sum = 0.0;
+        grenze += spb;
+        do { sum += (double)(fm_at(fm, mvp + rcount) - dc); rcount++; } while ((float)rcount < grenze);
+        if (symlen == 2) {
+            grenze += spb;
+            do { sum -= (double)(fm_at(fm, mvp + rcount) - dc); rcount++; } while ((float)rcount < grenze);
+        }
+        out[b] = sum >= 0 ? 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(CORR_THREADS) dft_corr_kernel(const DftParams p)
+{
+    extern __shared__ float smf[];
+    const int b = blockIdx.x, a = blockIdx.y, c = blockIdx.z, tid = threadIdx.x;
+    const HdrDev &h = p.hdr[a];
+    const int K = p.K, L = h.L, W = K + L, taps = p.lpFMtaps;
+    float *xw = smf;                                  /* [taps-1 + W]  raw window with (taps-1) samples of circular history */
+    float *xf = smf + (taps - 1 + W + 8);             /* padded: pad8(W + 16) */
+    float *mt = xf + pad8(W + 24) + 8;                /* [Lpad] match */
+    float *wl = mt + h.Lpad;                          /* [taps] FM low-pass */
+    __shared__ float red[CORR_THREADS / 32]; __shared__ int redi[CORR_THREADS / 32];
+    __shared__ float s_dc, s_best; __shared__ int s_mp;
+
+    const float *fm = (h.use_raw ? p.fm_raw : p.fm_filt) + (long long)c * p.nsamp;
+    /* the reference triggers after n = (b+1)(K-4) samples: pos = sample_out = n-1-delay (dft_detect.c:813-816,1498) */
+    const long long n_trig = (long long)(b + 1) * (K - 4), pos = n_trig - 1 - p.delay, w0 = pos - (W - 1);
+    for (int i = tid; i < W; i += CORR_THREADS) xw[taps - 1 + i] = fm_at(fm, w0 + i);         /* :376 (ring slots never written are 0) */
+    for (int i = tid; i < h.Lpad; i += CORR_THREADS) mt[i] = p.match[h.match_off + i];
+    for (int i = tid; i < taps; i += CORR_THREADS) wl[i] = p.ws_lpFM[h.lpFM * taps + i];
+    __syncthreads();
+    /* DC over the last 2L samples of the window (:388-391); X[0] -= N*dc*0.98 == subtract 0.98*dc from all N points */
+    float dc = 0.0f;
+    if (p.opt_dc) {
+        float s = 0.0f;
+        for (int i = K - L + tid; i < K + L; i += CORR_THREADS) s += xw[taps - 1 + i];
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if ((tid & 31) == 0) red[tid >> 5] = s;
+        __syncthreads();
+        if (tid == 0) { float t = 0; for (int w = 0; w < CORR_THREADS / 32; ++w) t += red[w]; s_dc = (float)((double)t / (2.0 * (double)(float)L)); }
+        __syncthreads();
+        dc = s_dc;
+    }
+    const float sub = (float)((double)dc * 0.98);
+    /* circular history: the points before the window are the zero padding of the N-point buffer, also shifted by -0.98dc */
+    for (int i = tid; i < taps - 1 + W; i += CORR_THREADS) xw[i] = (i < taps - 1 ? 0.0f : xw[i]) - sub;
+    __syncthreads();
+    /* FM low-pass as circular convolution with the taps (X *= WS, :396): xf[n] = sum_k wl[k] x'[n-k] */
+    for (int n = tid; n < W + 16; n += CORR_THREADS) {
+        float acc = 0.0f;
+        if (n < W) {
+            const float *xp = xw + taps - 1 + n;
+#pragma unroll 8
+            for (int k = 0; k < taps; ++k) acc = fmaf(wl[k], xp[-k], acc);
+        }
+        xf[pad8(n)] = acc;                                                    /* zeros beyond the window: tile overrun reads */
+    }
+    __syncthreads();
+    /* correlation: corr[lag] = sum_t xf[lag+t]*match[t], lag = i-(L-1) in [0, K]  (Z = X*Fm, :403-404) */
+    const int nlag = K + 1;
+    float best = -1.0f, bestv = 0.0f; int besti = -1;
+    for (int lag0 = tid * CORR_R; lag0 < nlag; lag0 += CORR_THREADS * CORR_R) {
+        float acc[CORR_R], xs[CORR_R];
+#pragma unroll
+        for (int r = 0; r < CORR_R; ++r) { acc[r] = 0.0f; xs[r] = xf[pad8(lag0 + r)]; }
+        for (int t0 = 0; t0 < h.Lpad; t0 += CORR_R) {
+            const int nb = pad8(lag0 + t0 + CORR_R);                          /* lag0+t0+8 is a multiple of 8: contiguous run of 8 */
+#pragma unroll
+            for (int u = 0; u < CORR_R; ++u) {
+                const float m = mt[t0 + u];
+#pragma unroll
+                for (int r = 0; r < CORR_R; ++r) acc[r] = fmaf(xs[(u + r) & (CORR_R - 1)], m, acc[r]);
+                xs[u] = xf[nb + u];                                           /* slide: slot u now holds sample lag0+t0+8+u */
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < CORR_R; ++r) {
+            const int lag = lag0 + r;
+            if (lag < nlag) { const float v2 = acc[r] * acc[r]; if (v2 > best) { best = v2; bestv = acc[r]; besti = lag; } }
+        }
+    }
+    /* first maximum of corr^2 (strict >, ascending lag, :413-421): larger value wins, ties -> smaller lag.
+       The reference starts from mx2 = 0, so an all-zero window yields mp = -1. */
+    if (!(best > 0.0f)) { best = 0.0f; besti = 0x7fffffff; }
+    for (int o = 16; o; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o), ov = __shfl_xor_sync(0xffffffffu, bestv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+        if (ob > best || (ob == best && oi < besti)) { best = ob; bestv = ov; besti = oi; }
+    }
+    __shared__ float redv[CORR_THREADS / 32];
+    if ((tid & 31) == 0) { red[tid >> 5] = best; redv[tid >> 5] = bestv; redi[tid >> 5] = besti; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < CORR_THREADS / 32; ++w)
+            if (red[w] > best || (red[w] == best && redi[w] < besti)) { best = red[w]; bestv = redv[w]; besti = redi[w]; }
+        s_mp = (best > 0.0f) ? besti + (L - 1) : -1; s_best = bestv;
+    }
+    __syncthreads();
+    const int mp = s_mp;
+    BlkRes r; r.score = 0.0f; r.pos = 0; r.dc = dc; r.mp = mp; r.herrs = 99; r.m10 = 0;
+    if (mp == L - 1 || mp == K + L - 1) r.mp = -4;                            /* Randwert, :422 */
+    float nrm = 0.0f;
+    if (r.mp > 0) {                                                          /* xnorm over the L filtered samples under the template (:427-429) */
+        for (int i = tid; i < L; i += CORR_THREADS) { const float v = xf[pad8(mp - i)]; nrm = fmaf(v, v, nrm); }
+        for (int o = 16; o; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+    }
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = nrm;
+    __syncthreads();
+    if (tid == 0) {
+        if (r.mp > 0) {
+            double t = 0; for (int w = 0; w < CORR_THREADS / 32; ++w) t += red[w];
+            r.score = (float)((double)s_best / sqrt(t));
+            const long long mpos = w0 + mp - taps / 2;                        /* :425,433 */
+            r.pos = (unsigned)mpos;
+            if (r.score > h.thres || r.score < -h.thres) {                    /* candidate: headcmp (:866-901) */
+                const float *raw = (h.use_raw ? p.fm_raw : p.fm_filt) + (long long)c * p.nsamp;
+                unsigned char bits[96]; unsigned rc = 0; float gr = 0.0f;
+                const float hdc = p.opt_dc ? dc : 0.0f;
+                slice_bits(raw, mpos + 1 - (int)(h.hLen * h.spb), h.spb, hdc, 1, h.hLen, rc, gr, bits);
+                const int inv = r.score < 0;
+                int errs = 0;
+                for (int i = 0; i < h.hLen; ++i) errs += ((bits[i] ^ inv) != h.bits[i]);
+                r.herrs = errs;
+                if (h.j == 6) {                                              /* frm_M10 (:932-965): Manchester bits after the header */
+                    const int ofs = (h.hLen - 28) / 2;
+                    unsigned char mb; unsigned char bit0 = inv ? 1 : 0; unsigned bytes = 0; unsigned rc2 = 0; float gr2 = 0.0f;
+                    for (int q = 0; q < 16; ++q) {
+                        if (q < ofs) mb = h.bits[28 + 2 * q] ^ inv;
+                        else slice_bits(raw, mpos, h.spb, hdc, 2, 1, rc2, gr2, &mb);
+                        const unsigned fb = 1u ^ (bit0 ^ mb);
+                        bytes = (bytes << 1) | fb;
+                        bit0 = mb;
+                    }
+                    r.m10 = bytes;
+                }
+            }
+        }
+        p.res[((long long)c * p.nblk + b) * p.nact + a] = r;
+    }
+}
+
+/* =============================== host side =================================================================== */
+struct b200dft {
+    int sr, opt_dc, nchan, device; double bw_khz;
+    int N, K, L, M, delay, lpIQtaps, lpFMtaps, nact, maxcnt;
+    std::vector<HdrDev> hdr; std::vector<int> act;      /* active header rows */
+    float spb[NRS]; int hLen[NRS], Lj[NRS];
+    float *d_ws_lpIQ = 0, *d_ws_lpFM = 0, *d_match = 0; HdrDev *d_hdr = 0;
+    float2 *d_avg = 0; float *d_fm_filt = 0, *d_fm_raw = 0; BlkRes *d_res = 0; void *d_iq = 0;
+    long long cap_samp = 0, cap_iq_bytes = 0; int cap_blk = 0, cap_avg = 0;
+    size_t corr_smem_max = 0;
+    cudaStream_t stream = 0; cudaEvent_t ev[4] = {0, 0, 0, 0};
+    long launches = 0; bool timed = false;
+};
+
+static double sinc_(double x) { return x == 0 ? 1 : sin(M_PI * x) / (M_PI * x); }
+static int lowpass_init(float f, int taps, std::vector<float> &ws)     /* dft_detect.c:665-697 */
+{
+    if (taps % 2 == 0) taps++;
+    if (taps < 1) taps = 1;
+    ws.assign(taps, 0.0f);
+    double norm = 0;
+    for (int n = 0; n < taps; n++) {
+        double w = 7938 / 18608.0 - 9240 / 18608.0 * cos(2 * M_PI * n / (taps - 1)) + 1430 / 18608.0 * cos(4 * M_PI * n / (taps - 1));
+        double hh = 2 * f * sinc_(2 * f * (n - (taps - 1) / 2));
+        ws[n] = w * hh;
+        norm += ws[n];
+    }
+    for (int n = 0; n < taps; n++) ws[n] /= norm;
+    return taps;
+}
+static double Qf(double x) { return 0.5 - 0.5 * erf(x / 1.4142135624); }
+static double pulse(double t, double sigma) { return Qf((t - 0.5) / sigma) - Qf((t + 0.5) / sigma); }
+
+extern "C" int b200dft_create(b200dft_t **out, int sample_rate, double bw_khz, int opt_dc, int nchan, int device)
+{
+    if (!out || sample_rate < 1 || nchan <= 0) return fail(B200DFT_EINVAL, "bad arguments");
+    if (!(bw_khz * 1e3 > 100.0)) return fail(B200DFT_EINVAL, "--bw <kHz> is required (single IF filter mode, dft_detect.c:1132-1137)");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail(B200DFT_ECUDA, "no CUDA device: libb200dft has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(B200DFT_ERANGE, "device");
+    CK(cudaSetDevice(device));
+    b200dft *h = new b200dft();
+    h->sr = sample_rate; h->opt_dc = opt_dc ? 1 : 0; h->nchan = nchan; h->device = device; h->bw_khz = bw_khz;
+    const int sr = sample_rate;
+    /* init_buffers(), --iq branch (dft_detect.c:1113-1156) */
+    std::vector<float> wfm0, wfm1, wiq;
+    int taps = 4 * sr / 2e3; if (taps % 2 == 0) taps++;
+    taps = lowpass_init(4e3f / (float)sr, taps, wfm0);
+    taps = lowpass_init(10e3f / (float)sr, taps, wfm1);
+    h->lpFMtaps = taps;
+    taps = 4 * sr / 4e3; if (taps % 2 == 0) taps++;
+    const float set_lpIQ = bw_khz * 1e3;
+    taps = lowpass_init(set_lpIQ / (float)sr / 2.0, taps, wiq);
+    h->lpIQtaps = taps;
+    if (taps > 256) { delete h; return fail(B200DFT_EINVAL, "IF filter too long"); }
+    h->maxcnt = sr / 32;
+    int hLenMax = 0, Lmax = 0;
+    for (int j = 0; j < NRS; j++) {                                          /* :1175-1184 */
+        h->spb[j] = sr / (float)HDR[j].sps;
+        h->hLen[j] = strlen(HDR[j].header);
+        h->Lj[j] = h->hLen[j] * h->spb[j] + 0.5;
+        if (j != SKIP_A && j != SKIP_B) { if (h->hLen[j] > hLenMax) hLenMax = h->hLen[j]; if (h->Lj[j] > Lmax) Lmax = h->Lj[j]; }
+    }
+    int L = 2 * Lmax, M = 3 * L, p2 = 1;
+    while (p2 < M) p2 <<= 1;
+    while (p2 < 0x2000) p2 <<= 1;
+    h->N = p2; h->K = p2 - L; h->L = L; h->delay = L / 16; h->M = p2 + h->delay + 8;
+    /* matched filters (:1223-1259), time domain only: the reference's m[L-1-i] = match[i] reversal + FFT product
+       is the correlation sum_t x[lag+t]*match[t] evaluated directly by the kernel */
+    std::vector<float> match_all; std::vector<float> match(L + 1);
+    for (int j = 0; j <= IDX_IMETAFSK; j++) {
+        if (j == SKIP_A || j == SKIP_B) continue;
+        const char *bits = HDR[j].header; const float spb = h->spb[j]; const int Lj = h->Lj[j];
+        if (h->K + Lj > h->N) continue;
+        const double sigma = sqrt(log(2)) / (2 * M_PI * HDR[j].BT);
+        for (int i = 0; i < Lj; i++) {
+            int pos = i / spb;
+            double t = (i - pos * spb) / spb - 0.5;
+            double bb = ((bits[pos] & 0x1) - 0.5) * 2.0 * pulse(t, sigma);
+            if (pos > 0) bb += ((bits[pos - 1] & 0x1) - 0.5) * 2.0 * pulse(t + 1, sigma);
+            if (pos < hLenMax - 1) bb += ((bits[pos + 1] & 0x1) - 0.5) * 2.0 * pulse(t - 1, sigma);   /* global hLen: :1249 */
+            match[i] = bb;
+        }
+        double n2 = 0; for (int i = 0; i < Lj; i++) n2 += (double)match[i] * match[i];
+        const float nm = sqrt(n2);
+        for (int i = 0; i < Lj; i++) match[i] /= nm;
+        HdrDev hd; memset(&hd, 0, sizeof hd);
+        hd.j = j; hd.L = Lj; hd.Lpad = (Lj + CORR_R - 1) / CORR_R * CORR_R; hd.hLen = h->hLen[j]; hd.use_raw = HDR[j].lpIQ == 3;
+        hd.lpFM = HDR[j].lpFM; hd.match_off = (int)match_all.size(); hd.spb = spb; hd.thres = HDR[j].thres;
+        for (int i = 0; i < hd.hLen; i++) hd.bits[i] = bits[i] & 1;
+        for (int i = 0; i < hd.Lpad; i++) match_all.push_back(i < Lj ? match[i] : 0.0f);
+        h->hdr.push_back(hd); h->act.push_back(j);
+        size_t sm = ((size_t)(h->lpFMtaps - 1 + h->K + Lj + 8) + (size_t)(h->K + Lj + 24 + ((h->K + Lj + 24) >> 3)) + 8 + hd.Lpad + h->lpFMtaps) * 4;
+        if (sm > h->corr_smem_max) h->corr_smem_max = sm;
+    }
+    h->nact = (int)h->hdr.size();
+    int maxsmem = 0;
+    CK(cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    if (h->corr_smem_max + 1024 > (size_t)maxsmem) { delete h; return fail(B200DFT_EINVAL, "correlator window does not fit shared memory"); }
+    CK(cudaFuncSetAttribute(dft_corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->corr_smem_max));
+    std::vector<float> wfm(2 * h->lpFMtaps);
+    for (int i = 0; i < h->lpFMtaps; i++) { wfm[i] = wfm0[i]; wfm[h->lpFMtaps + i] = wfm1[i]; }
+    CK(cudaMalloc(&h->d_ws_lpIQ, wiq.size() * 4)); CK(cudaMemcpy(h->d_ws_lpIQ, wiq.data(), wiq.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&h->d_ws_lpFM, wfm.size() * 4)); CK(cudaMemcpy(h->d_ws_lpFM, wfm.data(), wfm.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&h->d_match, match_all.size() * 4)); CK(cudaMemcpy(h->d_match, match_all.data(), match_all.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&h->d_hdr, h->hdr.size() * sizeof(HdrDev))); CK(cudaMemcpy(h->d_hdr, h->hdr.data(), h->hdr.size() * sizeof(HdrDev), cudaMemcpyHostToDevice));
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; i++) CK(cudaEventCreate(&h->ev[i]));
+    *out = h;
+    return B200DFT_OK;
+}
+
+extern "C" void b200dft_destroy(b200dft_t *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device); cudaDeviceSynchronize();
+    void *ptrs[] = {h->d_ws_lpIQ, h->d_ws_lpFM, h->d_match, h->d_hdr, h->d_avg, h->d_fm_filt, h->d_fm_raw, h->d_res, h->d_iq};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    for (int i = 0; i < 4; i++) cudaEventDestroy(h->ev[i]);
+    cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int b200dft_info(const b200dft_t *h, b200dft_info_t *info)
+{
+    if (!h || !info) return fail(B200DFT_EINVAL, "null");
+    info->sample_rate = h->sr; info->N_DFT = h->N; info->K = h->K; info->L = h->L; info->M = h->M; info->delay = h->delay;
+    info->lpIQtaps = h->lpIQtaps; info->lpFMtaps = h->lpFMtaps; info->nhdr_active = h->nact; info->nchan = h->nchan;
+    return B200DFT_OK;
+}
+
+/* The decision loop of main() (dft_detect.c:1498-1652) over the per-block records of one channel. */
+static void decide_channel(const b200dft *h, const BlkRes *res, int nblk, long nsamp_eff, int opt_cont, b200dft_result_t *out)
+{
+    const int nact = h->nact;
+    float mv[NRS]; unsigned mv_pos[NRS], mv0_pos[NRS]; int mp[NRS]; float dcv[NRS], dfv[NRS];
+    const char *type[NRS]; int tn[NRS];
+    for (int j = 0; j < NRS; j++) { mv[j] = 0; mv_pos[j] = 0; mp[j] = 0; dcv[j] = dfv[j] = 0; type[j] = HDR[j].type; tn[j] = HDR[j].tn; }
+    int j_max = 0; float mv_max = 0; int header_found = 0; unsigned frm2 = 0;
+    memset(out, 0, sizeof *out);
+    (void)nsamp_eff;
+    for (int b = 0; b < nblk; b++) {
+        const BlkRes *rb = res + (size_t)b * nact;
+        for (int a = 0; a < nact; a++) {
+            const int j = h->act[a];
+            mv0_pos[j] = mv_pos[j];
+            mp[j] = rb[a].mp; dcv[j] = rb[a].dc;
+            if (rb[a].mp > 0) { mv[j] = rb[a].score; mv_pos[j] = rb[a].pos; }          /* getCorrDFT leaves them untouched on failure */
+            if (h->opt_dc) dfv[j] = dcv[j] / (2.0 * FM_GAIN * 1);
+        }
+        header_found = 0;
+        for (int a = 0; a < nact; a++) {
+            const int j = h->act[a];
+            if (!(mp[j] > 0 && (mv[j] > HDR[j].thres || mv[j] < -HDR[j].thres))) continue;
+            if (!(mv_pos[j] > mv0_pos[j])) continue;
+            if (!(rb[a].herrs < HDR[j].herrs)) continue;
+            if (j == 6) {                                                             /* M10 / M20 (:1526-1540) */
+                const unsigned bytes = rb[a].m10; int hwt = 0; for (int q = 0; q < 4; q++) hwt += (bytes >> q) & 1;
+                if (hwt < 2 || (hwt == 2 && (bytes & 0xF0) == 0x20)) { type[j] = "M20"; tn[j] = 6; } else { type[j] = "M10"; tn[j] = 5; }
+                frm2 = bytes;
+            }
+            if (j == IDX_IMETAFSK) {
+                /* iMet AFSK preamble: the reference reads one more second and compares the 2200/2400/800 Hz FM-audio
+                   power to tell IMET4/IMET1RS from IMET1AB (:1542-1607).  Not implemented on the device path yet:
+                   the candidate is dropped exactly as when that test fails (mv[j] = 0). */
+                mv[j] = 0.0f;
+                continue;
+            }
+            header_found = 1;
+            if (mv[j] > HDR[j].thres || mv[j] < -HDR[j].thres) {
+                if (out->ndet < B200DFT_MAXDET) {
+                    b200dft_det_t *d = &out->dets[out->ndet];
+                    d->hdr = j; d->tn = tn[j]; d->score = mv[j]; d->pos = mv_pos[j]; d->df_hz = dfv[j] * h->sr; d->m10 = frm2 & 0xFFFF;
+                    strncpy(d->type, type[j], sizeof d->type - 1);
+                }
+                out->ndet++;
+                if (j == 6) frm2 = 0;
+            }
+            if (fabsf(mv_max) < fabsf(mv[j])) { mv_max = mv[j]; j_max = j; }
+        }
+        if (header_found && !opt_cont) break;
+        header_found = 0;
+        for (int j = 0; j < NRS; j++) mv[j] = 0.0f;
+    }
+    if (mv_max) header_found = (mv_max < 0 && j_max < 3) ? -1 : 1; else header_found = 0;
+    out->exit_code = header_found * tn[j_max];
+}
+
+static int run_common(b200dft *h, const void *d_iq, int fmt, long in_stride, long nsamp, int opt_cont, double tl, b200dft_result_t *res)
+{
+    /* -t: the reference stops once sample_in > (tl+1)*sr, i.e. it reads floor((tl+1)*sr)+1 samples at most (:1494) */
+    long neff = nsamp;
+    if (tl > 0) { const long lim = (long)floor((tl + 1) * h->sr); if (neff > lim) neff = lim; }
+    const int nblk = (int)(neff / (h->K - 4));
+    const int navg = (int)(neff / h->maxcnt) + 2;
+    if (neff > h->cap_samp) {
+        if (h->d_fm_filt) cudaFree(h->d_fm_filt); if (h->d_fm_raw) cudaFree(h->d_fm_raw);
+        CK(cudaMalloc(&h->d_fm_filt, (size_t)h->nchan * neff * 4)); CK(cudaMalloc(&h->d_fm_raw, (size_t)h->nchan * neff * 4));
+        h->cap_samp = neff;
+    }
+    if (navg > h->cap_avg) { if (h->d_avg) cudaFree(h->d_avg); CK(cudaMalloc(&h->d_avg, (size_t)h->nchan * navg * sizeof(float2))); h->cap_avg = navg; }
+    if (nblk > h->cap_blk) { if (h->d_res) cudaFree(h->d_res); CK(cudaMalloc(&h->d_res, (size_t)h->nchan * nblk * h->nact * sizeof(BlkRes))); h->cap_blk = nblk; }
+    DftParams p; memset(&p, 0, sizeof p);
+    p.nchan = h->nchan; p.nact = h->nact; p.N = h->N; p.K = h->K; p.L = h->L; p.lpIQtaps = h->lpIQtaps; p.lpFMtaps = h->lpFMtaps;
+    p.delay = h->delay; p.opt_dc = h->opt_dc; p.maxcnt = h->maxcnt; p.nblk = nblk; p.navg = navg; p.nsamp = neff; p.in_stride = in_stride;
+    p.fmt = fmt; p.iq = d_iq; p.ws_lpIQ = h->d_ws_lpIQ; p.ws_lpFM = h->d_ws_lpFM; p.match = h->d_match; p.hdr = h->d_hdr;
+    p.avg = h->d_avg; p.fm_filt = h->d_fm_filt; p.fm_raw = h->d_fm_raw; p.res = h->d_res;
+    cudaStream_t s = h->stream;
+    CK(cudaEventRecord(h->ev[0], s));
+    if (neff > 0) {
+        dim3 g0((unsigned)(navg - 1), h->nchan);
+        dft_dcavg_kernel<<<g0, 128, 0, s>>>(p);
+        dim3 g1((unsigned)((neff + FRONT_TILE - 1) / FRONT_TILE), h->nchan);
+        const size_t sm1 = (size_t)(2 * FRONT_TILE + h->lpIQtaps + 1) * sizeof(float2);
+        dft_front_kernel<<<g1, FRONT_TILE, sm1, s>>>(p);
+        h->launches += 2;
+    }
+    CK(cudaEventRecord(h->ev[1], s));
+    if (nblk > 0) {
+        dim3 g2(nblk, h->nact, h->nchan);
+        dft_corr_kernel<<<g2, CORR_THREADS, h->corr_smem_max, s>>>(p);
+        h->launches += 1;
+    }
+    CK(cudaEventRecord(h->ev[2], s));
+    CK(cudaGetLastError());
+    std::vector<BlkRes> hres((size_t)h->nchan * nblk * h->nact);
+    if (nblk > 0) CK(cudaMemcpyAsync(hres.data(), h->d_res, hres.size() * sizeof(BlkRes), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    h->timed = true;
+    for (int c = 0; c < h->nchan; c++) decide_channel(h, hres.data() + (size_t)c * nblk * h->nact, nblk, neff, opt_cont, &res[c]);
+    return B200DFT_OK;
+}
+
+extern "C" int b200dft_run_device(b200dft_t *h, const void *d_iq, int fmt, long in_stride, long nsamp, int opt_cont, double tl,
+                                  b200dft_result_t *res)
+{
+    if (!h || !d_iq || !res) return fail(B200DFT_EINVAL, "null");
+    if (fmt < 0 || fmt > 2 || nsamp < 0) return fail(B200DFT_ERANGE, "fmt/nsamp");
+    CK(cudaSetDevice(h->device));
+    return run_common(h, d_iq, fmt, in_stride, nsamp, opt_cont, tl, res);
+}
+
+extern "C" int b200dft_run_host(b200dft_t *h, const void *h_iq, int fmt, long in_stride, long nsamp, int opt_cont, double tl,
+                                b200dft_result_t *res)
+{
+    if (!h || !h_iq || !res) return fail(B200DFT_EINVAL, "null");
+    if (fmt < 0 || fmt > 2 || nsamp < 0) return fail(B200DFT_ERANGE, "fmt/nsamp");
+    CK(cudaSetDevice(h->device));
+    const int es = fmt == 1 ? 8 : (fmt == 0 ? 4 : 2);
+    const size_t need = (size_t)h->nchan * nsamp * es;
+    if ((long long)need > h->cap_iq_bytes) { if (h->d_iq) cudaFree(h->d_iq); CK(cudaMalloc(&h->d_iq, need + 16)); h->cap_iq_bytes = need; }
+    if (nsamp > 0)
+        CK(cudaMemcpy2DAsync(h->d_iq, (size_t)nsamp * es, h_iq, (size_t)in_stride * es, (size_t)nsamp * es, h->nchan, cudaMemcpyHostToDevice, h->stream));
+    return run_common(h, h->d_iq, fmt, nsamp, nsamp, opt_cont, tl, res);
+}
+
+extern "C" long b200dft_launch_count(const b200dft_t *h) { return h ? h->launches : 0; }
+extern "C" int b200dft_last_kernel_ms(b200dft_t *h, float *front_ms, float *corr_ms)
+{
+    if (!h || !h->timed) return fail(B200DFT_EINVAL, "no run yet");
+    float a = 0, b = 0;
+    CK(cudaEventElapsedTime(&a, h->ev[0], h->ev[1])); CK(cudaEventElapsedTime(&b, h->ev[1], h->ev[2]));
+    if (front_ms) *front_ms = a; if (corr_ms) *corr_ms = b;
+    return B200DFT_OK;
+}

@@ -1,0 +1,146 @@
+"""Host-side mirror of the reference detector CLI (scan/dft_detect.c) over libb200dft.so.
+
+``DftDetectBatch(sample_rate, bw_khz, dc, nchan)`` is "``nchan`` dft_detect processes with the arguments
+``--iq --bw <bw_khz> [--dc] - <sample_rate> <bits>``"; ``run()`` returns for every channel what that process would
+have printed (type, score, sample position, frequency offset) and its exit code (+-type number,
+dft_detect.c:1660-1666).  ``format_lines()`` reproduces the stdout text parsed by auto_rx
+(auto_rx/autorx/scan.py:227-410).  No CPU fallback; nothing under oracle/ is used here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200dft.so")
+_FMT = {np.dtype(np.int16): 0, np.dtype(np.float32): 1, np.dtype(np.uint8): 2}
+
+
+class B200DftError(RuntimeError):
+    pass
+
+
+class _Det(C.Structure):
+    _fields_ = [("hdr", C.c_int), ("tn", C.c_int), ("score", C.c_float), ("pos", C.c_uint32), ("df_hz", C.c_float),
+                ("m10", C.c_uint32), ("type", C.c_char * 12)]
+
+
+class _Res(C.Structure):
+    _fields_ = [("exit_code", C.c_int), ("ndet", C.c_int), ("dets", _Det * 16)]
+
+
+class _Info(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("sample_rate", "N_DFT", "K", "L", "M", "delay", "lpIQtaps", "lpFMtaps", "nhdr_active", "nchan")]
+
+
+@dataclass
+class Detection:
+    type: str
+    score: float
+    pos: int
+    df_hz: float
+    tn: int
+    m10: int
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B200DftError(f"{LIB_PATH} not built (run __graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        L.b200dft_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_double, C.c_int, C.c_int, C.c_int]
+        L.b200dft_destroy.argtypes = [C.c_void_p]
+        L.b200dft_destroy.restype = None
+        L.b200dft_info.argtypes = [C.c_void_p, C.POINTER(_Info)]
+        L.b200dft_last_error.restype = C.c_char_p
+        L.b200dft_run_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_long, C.c_long, C.c_int, C.c_double, C.c_void_p]
+        L.b200dft_run_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_long, C.c_long, C.c_int, C.c_double, C.c_void_p]
+        L.b200dft_launch_count.argtypes = [C.c_void_p]
+        L.b200dft_launch_count.restype = C.c_long
+        L.b200dft_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        _lib = L
+    return _lib
+
+
+def _ck(rc: int) -> None:
+    if rc != 0:
+        raise B200DftError(f"libb200dft error {rc}: {lib().b200dft_last_error().decode()}")
+
+
+class DftDetectBatch:
+    def __init__(self, sample_rate: int = 48000, bw_khz: float = 15.0, dc: bool = True, nchan: int = 1, device: int = 0):
+        self.L = lib()
+        self.h = C.c_void_p()
+        _ck(self.L.b200dft_create(C.byref(self.h), sample_rate, float(bw_khz), int(dc), nchan, device))
+        info = _Info()
+        _ck(self.L.b200dft_info(self.h, C.byref(info)))
+        self.info = info
+        self.nchan, self.sample_rate, self.dc = nchan, sample_rate, dc
+        self.K, self.N_DFT = info.K, info.N_DFT
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.b200dft_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _collect(self, res):
+        out = []
+        for c in range(self.nchan):
+            r = res[c]
+            dets = [Detection(r.dets[i].type.decode(), r.dets[i].score, r.dets[i].pos, r.dets[i].df_hz, r.dets[i].tn, r.dets[i].m10)
+                    for i in range(min(r.ndet, 16))]
+            out.append((r.exit_code, dets))
+        return out
+
+    def run(self, iq: np.ndarray, cont: bool = False, tl: float = -1.0):
+        """iq: [nchan, nsamp, 2] int16 / float32 / uint8 host array -> [(exit_code, [Detection...])] per channel."""
+        iq = np.ascontiguousarray(iq)
+        fmt = _FMT[iq.dtype]
+        iq = iq.reshape(self.nchan, -1)
+        nsamp = iq.shape[1] // 2
+        res = (_Res * self.nchan)()
+        _ck(self.L.b200dft_run_host(self.h, iq.ctypes.data, fmt, nsamp, nsamp, int(cont), float(tl), res))
+        return self._collect(res)
+
+    def run_device(self, d_iq, fmt: str, nsamp: int, cont: bool = False, tl: float = -1.0, in_stride: int | None = None):
+        f = {"cs16": 0, "f32": 1, "cu8": 2}[fmt]
+        res = (_Res * self.nchan)()
+        ptr = d_iq.data_ptr() if hasattr(d_iq, "data_ptr") else int(d_iq)
+        _ck(self.L.b200dft_run_device(self.h, C.c_void_p(ptr), f, in_stride or nsamp, nsamp, int(cont), float(tl), res))
+        return self._collect(res)
+
+    def kernel_ms(self):
+        a, b = C.c_float(0), C.c_float(0)
+        _ck(self.L.b200dft_last_kernel_ms(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    @property
+    def launches(self) -> int:
+        return int(self.L.b200dft_launch_count(self.h))
+
+    def format_lines(self, dets, verbose: bool = False) -> str:
+        """The stdout text of the reference (dft_detect.c:1620-1634)."""
+        out = []
+        for d in dets:
+            if verbose:
+                out.append(f"sample: {d.pos}")
+            ln = f"{d.type}: {d.score:.4f}"
+            if d.type.startswith(("M10", "M20")) and verbose:
+                ln += f" [{d.m10 & 0xFFFF:04X}]"
+            if self.dc:
+                ln += f" , {d.df_hz:+.1f}Hz"
+            out.append(ln)
+        return "\n".join(out) + ("\n" if out else "")

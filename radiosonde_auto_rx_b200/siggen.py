@@ -93,3 +93,62 @@ def fsk_batch(base_seed: int, nchan: int, nsamp: int, workers: int = 8, **kw) ->
     with ThreadPoolExecutor(max_workers=workers) as ex:
         list(ex.map(one, range(nchan)))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# dft_detect workloads: FM (GFSK) carriers whose bit stream contains the sonde-type header
+# ---------------------------------------------------------------------------------------------------
+# (sps, header) of the reference's header bank, scan/dft_detect.c:43-126,177-194 (index = rs_hdr[] row)
+HEADER_BANK = {
+    "DFM9": (0, 2500, "10011010100110010101101001010101"),
+    "RS41": (1, 4800, RS41_HEADER),
+    "RS92": (2, 4800, "10100110011001101001" * 2 + "1010011001100110100110101010100110101001"),
+    "LMS6": (3, 4800, "0101011000001000" "0001110010010111" "0001101010100111" "0011110100111110"),
+    "IMET5": (4, 4800, "0000000001" "0101010101" "0001001001" "0001001001"),
+    "MK2LMS": (5, 9616, "0010100111" "0010100111" "0001001001" "0010010101"),
+    "M10": (6, 9608, "1001100110010100110010011001" "1010"),
+    "MEISEI": (7, 2400, "110011001101001101001101010100101010110010101010"),
+    "RD94RD41": (8, 4800, "10100110010110101001" "10010101011010010101" "10101001010101010101" "10011001010110101001"),
+    "MRZ": (9, 2400, "1001100110011001" "1001101010101010"),
+    "MTS01": (10, 1200, "10101010" "10101010" "10110100" "00101011"),
+    "WXR301": (12, 4800, "10101010" * 3 + "00101101" "11010100"),
+    "WXRPN9": (13, 5000, "10101010" * 3 + "11000001" "10010100"),
+}
+
+
+def fm_header_iq(seed: int, nsamp: int, kind: str, Fs: int = 48000, dev_hz: float = 2400.0, snr_db: float = 20.0,
+                 f_off: float | None = None, invert: bool = False, period_bits: int | None = None, amp: float = 8000.0,
+                 tail: str = "") -> np.ndarray:
+    """GFSK carrier at complex baseband whose bits are random except for `kind`'s header inserted every
+    `period_bits` bits (followed by `tail`, e.g. M10/M20 frame-type bits) -> cs16 [nsamp, 2].
+    SNR is carrier-to-noise in the full Fs bandwidth."""
+    rng = np.random.default_rng(seed)
+    _, sps, hdr = HEADER_BANK[kind]
+    spb = Fs / sps
+    nbits = int(nsamp / spb) + 8
+    bits = rng.integers(0, 2, size=nbits, dtype=np.uint8)
+    h = np.frombuffer((hdr + tail).encode(), dtype=np.uint8) - ord("0")
+    if period_bits is None:
+        period_bits = max(4 * len(h), int(0.25 * sps))
+    for s in range(int(rng.integers(len(h), period_bits)), nbits - len(h), period_bits):
+        bits[s:s + len(h)] = h
+    lvl = bits.astype(np.float64) * 2.0 - 1.0
+    if invert:
+        lvl = -lvl
+    t0 = float(rng.uniform(0, 1))
+    idx = (np.arange(nsamp, dtype=np.float64) / spb + t0).astype(np.int64)
+    f = lvl[idx]
+    # Gaussian-ish pulse shaping: moving average over ~0.6 bit (keeps the header eye open at every spb)
+    w = max(1, int(round(0.6 * spb)))
+    f = np.convolve(f, np.ones(w) / w, mode="same")
+    if f_off is None:
+        f_off = float(rng.uniform(-3000.0, 3000.0))
+    phase = 2.0 * np.pi * np.cumsum(dev_hz * f + f_off) / Fs + float(rng.uniform(0, 2 * np.pi))
+    np.remainder(phase, 2.0 * np.pi, out=phase)
+    sigma = amp / np.sqrt(2.0) / (10.0 ** (snr_db / 20.0))
+    out = rng.standard_normal((nsamp, 2), dtype=np.float32) * np.float32(sigma)
+    out[:, 0] += np.float32(amp) * np.cos(phase).astype(np.float32)
+    out[:, 1] += np.float32(amp) * np.sin(phase).astype(np.float32)
+    np.rint(out, out=out)
+    np.clip(out, -32768, 32767, out=out)
+    return out.astype(np.int16)

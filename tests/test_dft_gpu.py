@@ -1,0 +1,84 @@
+"""GPU parity: batched dft_detect (C-ABI) vs the oracle: identical type / sign / sample position / exit code,
+score within 2e-4 abs (the reference itself is -Ofast: float sums are not bit-reproducible), df within 0.2 Hz."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from radiosonde_auto_rx_b200 import dft, siggen
+
+pytestmark = pytest.mark.gpu
+SCORE_TOL, DF_TOL = 2e-4, 0.2
+
+
+def compare(got, exp_rc, exp_dets, tag=""):
+    rc, dets = got
+    assert rc == exp_rc, f"{tag}: exit code {rc} != {exp_rc}"
+    assert len(dets) == len(exp_dets), f"{tag}: {len(dets)} detections, oracle {len(exp_dets)}"
+    for d, e in zip(dets, exp_dets):
+        assert d.type == e[0] and d.pos == e[2], f"{tag}: {d} vs {e}"
+        assert abs(d.score - e[1]) < SCORE_TOL and (d.score < 0) == (e[1] < 0), f"{tag}: score {d.score} vs {e[1]}"
+        assert abs(d.df_hz - e[3]) < DF_TOL
+
+
+def build_channels(nsamp, kinds, seed=300):
+    chans, tags = [], []
+    for i, k in enumerate(kinds):
+        if k == "noise":
+            chans.append(siggen.noise_iq(seed + i, nsamp))
+        else:
+            tail = ""
+            if k == "M10":          # frame-type bits after the header decide M10 vs M20 (dft_detect.c:1526-1540)
+                tail = "0110010010011111" if i % 2 == 0 else "0100010100100000"
+                tail = "".join("10" if b == "1" else "01" for b in tail)
+            chans.append(siggen.fm_header_iq(seed + i, nsamp, k, snr_db=(12, 18, 25)[i % 3], invert=(i % 4 == 3), tail=tail))
+        tags.append(k)
+    return np.stack(chans), tags
+
+
+@pytest.mark.parametrize("cont", [True, False])
+def test_header_bank_matches_oracle(cuda, cont):
+    kinds = list(siggen.HEADER_BANK) + ["noise", "M10", "RS41"]
+    nsamp = 100_000
+    iq, tags = build_channels(nsamp, kinds)
+    b = dft.DftDetectBatch(48000, 15.0, True, nchan=len(kinds))
+    got = b.run(iq, cont=cont)
+    found = 0
+    for c, k in enumerate(kinds):
+        rc, dets, _ = po.dft_oracle_run(iq[c], 48000, 15.0, True, cont)
+        compare(got[c], rc, dets, f"{k}[{c}] cont={cont}")
+        found += len(dets) > 0
+    assert found >= len(siggen.HEADER_BANK)
+    fr, co = b.kernel_ms()
+    assert fr > 0 and co > 0 and b.launches == 3
+
+
+def test_time_limit_and_device_path(cuda):
+    import torch
+    kinds = ["RS41", "DFM9", "noise", "M10"]
+    iq, _ = build_channels(160_000, kinds, seed=500)
+    b = dft.DftDetectBatch(48000, 15.0, True, nchan=len(kinds))
+    d = torch.from_numpy(iq).cuda()
+    got = b.run_device(d, "cs16", iq.shape[1], cont=True, tl=1.5)
+    for c, k in enumerate(kinds):
+        rc, dets, _ = po.dft_oracle_run(iq[c], 48000, 15.0, True, True, 1.5)
+        compare(got[c], rc, dets, f"{k} tl=1.5")
+
+
+def test_no_dc_and_other_bandwidth(cuda):
+    kinds = ["RS41", "MEISEI", "LMS6"]
+    iq, _ = build_channels(90_000, kinds, seed=700)
+    for bw, dc in ((20.0, True), (15.0, False)):
+        b = dft.DftDetectBatch(48000, bw, dc, nchan=len(kinds))
+        got = b.run(iq, cont=True)
+        for c, k in enumerate(kinds):
+            rc, dets, _ = po.dft_oracle_run(iq[c], 48000, bw, dc, True)
+            compare(got[c], rc, dets, f"{k} bw={bw} dc={dc}")
+
+
+def test_output_text_matches_reference_format(cuda):
+    iq, _ = build_channels(60_000, ["RS41"], seed=900)
+    b = dft.DftDetectBatch(48000, 15.0, True, nchan=1)
+    rc, dets = b.run(iq, cont=False)[0]
+    txt = b.format_lines(dets)
+    typ, rest = txt.strip().split(":")
+    assert typ == "RS41" and rest.strip().endswith("Hz") and rc == 3

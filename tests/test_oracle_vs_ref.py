@@ -1,0 +1,63 @@
+"""CPU tests that PIN the oracle: our C restatements vs the UNMODIFIED reference compiled into oracle/_ref
+(fsk: bit-identical outputs and state; dft_detect: type/sign/position exact, score 1e-3).  Needs oracle/_ref,
+i.e. /root/reference at build time or the prebuilt files that travel with the tree."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from radiosonde_auto_rx_b200 import siggen
+
+needs_ref = pytest.mark.skipif(not po.ref_available(), reason="oracle/_ref not built and /root/reference absent")
+
+FSK_CASES = {
+    "rs41": (po.RS41, dict()),
+    "rs41_noise": (po.RS41, None),
+    "default_hard": (po.FskConfig(48000, 4800, 2, 10, 50, soft=False), dict(ppm=10.0)),
+    "rs92": (po.FskConfig(48000, 4800, 2, 10, 50, -20000, 20000), dict()),
+    "dfm_softinv": (po.FskConfig(50000, 2500, 2, 10, 50, -5000, 5000, softinv=True), dict(Fs=50000, Rs=2500, spacing=5000.0)),
+    "m10": (po.FskConfig(48080, 9616, 2, 5, 50, -10000, 10000), dict(Fs=48080, Rs=9616)),
+    "wxr301_mask": (po.FskConfig(96000, 4800, 2, 10, 50, -40000, 40000, 50000), dict(Fs=96000, Rs=4800, spacing=50000.0)),
+    "4fsk_mask": (po.FskConfig(48000, 4800, 4, 10, 50, -20000, 20000, mask=4800), dict(M=4, spacing=4800.0)),
+    "4fsk_peak_hard": (po.FskConfig(48000, 4800, 4, 10, 50, soft=False), dict(M=4, spacing=4800.0)),
+}
+
+
+@needs_ref
+@pytest.mark.parametrize("name", list(FSK_CASES))
+def test_fsk_oracle_bit_identical_to_reference(built, name):
+    cfg, kw = FSK_CASES[name]
+    n = 200_000
+    iq = siggen.noise_iq(77, n) if kw is None else siggen.fsk_iq(40 + len(name), n, ebno_db=9.0, **kw)
+    out, cons, recs = po.Oracle(cfg).run_stream(iq)
+    rout, rcons, rrec, rSf = po.ref_run_stream(cfg, iq)
+    assert cons == rcons and len(recs) == len(rrec) > 0
+    assert out.tobytes() == rout.tobytes()
+    assert np.array_equal(recs["nin_next"], rrec[:, 1].astype(np.int32))
+    for k, col in (("norm_rx_timing", 2), ("ppm", 3), ("EbNodB", 4), ("snr_est", 5)):
+        assert np.array_equal(recs[k].view(np.uint32), rrec[:, col].view(np.uint32)), k
+    assert np.array_equal(recs["f_est"].view(np.uint32), rrec[:, 6:10].view(np.uint32))
+
+
+@needs_ref
+def test_fsk_oracle_matches_reference_cli_bytes(built):
+    """The actual reference executable on stdin/stdout (the drop-in surface) vs the oracle's frame pump."""
+    cfg = po.RS41
+    iq = siggen.fsk_iq(5, 100_000, ebno_db=12.0, ppm=25.0)
+    out, _, _ = po.Oracle(cfg).run_stream(iq)
+    so, se, rc = po.ref_cli_fsk_demod(cfg, iq.tobytes())
+    assert rc == 0 and so == out.tobytes()
+    assert se.startswith(b"Setting estimator limits to -5000 to 5000 Hz.")
+
+
+@needs_ref
+@pytest.mark.parametrize("kind", list(siggen.HEADER_BANK) + ["noise"])
+def test_dft_oracle_matches_reference_binary(built, kind):
+    n = 100_000
+    iq = siggen.noise_iq(9, n) if kind == "noise" else siggen.fm_header_iq(200 + len(kind), n, kind, snr_db=16.0)
+    rc, dets, _ = po.dft_oracle_run(iq, 48000, 15.0, True, True)
+    rrc, rdets = po.ref_cli_dft_detect(iq, 48000, 15.0, True, True)
+    assert rc == rrc and len(dets) == len(rdets)
+    if kind != "noise":
+        assert len(dets) > 0 and dets[0][0].startswith(kind[:3]) or kind == "M10"
+    for a, b in zip(dets, rdets):
+        assert a[0] == b[0] and a[2] == b[2] and abs(a[1] - b[1]) < 1e-3 and abs(a[3] - b[3]) < 0.2
