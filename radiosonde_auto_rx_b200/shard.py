@@ -1,0 +1,62 @@
+"""Multi-GPU plumbing for the channel-sharded path.
+
+The hot path partitions by channel: GPU g owns a contiguous block of narrowband IQ streams and their persistent
+demodulator state for ever; no data-path collective exists.  A collective is used only to DISTRIBUTE input when one
+rank holds a shared capture: ``scatter_capture`` (torch.distributed.scatter -- NCCL over NVLink on GPUs, gloo on CPU
+for the tests) hands every rank its [channels_g, nsamp, 2] slab; results (bits, detections) stay per rank and only
+tiny per-channel counters are gathered.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_range(nchan_total: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous channel block [lo, hi) owned by `rank`; sizes differ by at most one."""
+    base, rem = divmod(nchan_total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def scatter_capture(iq_root, nchan_total: int, nsamp: int, src: int = 0, device=None):
+    """Rank `src` passes the full capture (int16 [nchan_total, nsamp, 2], torch tensor or numpy); every rank gets its
+    shard as a torch tensor on `device`.  Shards are padded to equal size for the collective and trimmed after."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    per = -(-nchan_total // world)
+    lo, hi = shard_range(nchan_total, world, rank)
+    dev = device if device is not None else "cpu"
+    # collectives move raw bytes (gloo has no int16): view the slabs as uint8
+    recv = torch.empty((per, nsamp * 4), dtype=torch.uint8, device=dev)
+    chunks = None
+    if rank == src:
+        full = torch.as_tensor(np.ascontiguousarray(iq_root) if isinstance(iq_root, np.ndarray) else iq_root).to(dev)
+        chunks = []
+        for r in range(world):
+            a, b = shard_range(nchan_total, world, r)
+            t = torch.zeros((per, nsamp, 2), dtype=torch.int16, device=dev)
+            t[: b - a] = full[a:b]
+            chunks.append(t.view(torch.uint8).reshape(per, nsamp * 4))
+    dist.scatter(recv, chunks, src=src)
+    return recv.view(torch.int16).reshape(per, nsamp, 2)[: hi - lo]
+
+
+def gather_counts(local_counts, nchan_total: int, dst: int = 0, device=None):
+    """Per-channel int counters of every rank -> one [nchan_total] array on `dst` (None elsewhere)."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    per = -(-nchan_total // world)
+    dev = device if device is not None else "cpu"
+    t = torch.zeros(per, dtype=torch.int64, device=dev)
+    t[: len(local_counts)] = torch.as_tensor(np.asarray(local_counts, dtype=np.int64)).to(dev)
+    out = [torch.zeros_like(t) for _ in range(world)] if rank == dst else None
+    dist.gather(t, out, dst=dst)
+    if rank != dst:
+        return None
+    res = []
+    for r in range(world):
+        a, b = shard_range(nchan_total, world, r)
+        res.append(out[r][: b - a].cpu().numpy())
+    return np.concatenate(res)

@@ -1,0 +1,74 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in this directory by running the UNMODIFIED reference (oracle/_ref, compiled from
+/root/reference by oracle/Makefile) on small seeded inputs.  Run in the build container:
+
+    python tests/golden/make_golden.py
+
+Outputs (committed): golden_fsk.npz, golden_dft.json.  The inputs are regenerated from seeds by
+radiosonde_auto_rx_b200.siggen, so only outputs + an input checksum are stored.
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import pyoracle as po                      # noqa: E402
+from radiosonde_auto_rx_b200 import siggen             # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+FSK_CASES = {
+    # name: (FskConfig kwargs, siggen kwargs, nsamp)
+    "rs41_prod": (dict(Fs=48000, Rs=4800, M=2, P=5, Nsym=300, lower=-5000, upper=5000, mask=5000), dict(seed=11, ebno_db=10.0, ppm=35.0), 60000),
+    "rs41_noise": (dict(Fs=48000, Rs=4800, M=2, P=5, Nsym=300, lower=-5000, upper=5000, mask=5000), None, 40000),
+    "default_hard": (dict(Fs=48000, Rs=4800, M=2, P=10, Nsym=50, soft=False), dict(seed=12, ebno_db=9.0, ppm=-20.0), 30000),
+    "dfm_softinv": (dict(Fs=50000, Rs=2500, M=2, P=10, Nsym=50, lower=-5000, upper=5000, softinv=True), dict(seed=13, Fs=50000, Rs=2500, spacing=5000.0, ebno_db=12.0), 30000),
+    "4fsk_mask": (dict(Fs=48000, Rs=4800, M=4, P=10, Nsym=50, lower=-20000, upper=20000, mask=4800), dict(seed=14, M=4, spacing=4800.0, ebno_db=13.0), 30000),
+}
+DFT_CASES = {k: dict(seed=700 + i, kind=k, nsamp=60000, snr_db=16.0) for i, k in enumerate(["RS41", "DFM9", "M10", "MTS01", "WXR301", "noise"])}
+
+
+def fsk_input(name):
+    ck, sk, n = FSK_CASES[name]
+    if sk is None:
+        return siggen.noise_iq(99, n)
+    sk = dict(sk)
+    return siggen.fsk_iq(sk.pop("seed"), n, **sk)
+
+
+def dft_input(name):
+    c = DFT_CASES[name]
+    return siggen.noise_iq(c["seed"], c["nsamp"]) if c["kind"] == "noise" else siggen.fm_header_iq(c["seed"], c["nsamp"], c["kind"], snr_db=c["snr_db"])
+
+
+def main():
+    out = {}
+    for name, (ck, _, _) in FSK_CASES.items():
+        cfg = po.FskConfig(**ck)
+        iq = fsk_input(name)
+        so, se, rc = po.ref_cli_fsk_demod(cfg, iq.tobytes())          # the reference EXECUTABLE, stdin -> stdout
+        assert rc == 0
+        o, cons, recs, Sf = po.ref_run_stream(cfg, iq)                  # same modem through its C API, plus state
+        assert o.tobytes() == so
+        out[name + "/out"] = np.frombuffer(so, dtype=np.float32 if cfg.soft else np.uint8)
+        out[name + "/nin"] = recs[:, 1].astype(np.int32)
+        out[name + "/ppm"] = recs[:, 3].copy()
+        out[name + "/snr_est"] = recs[:, 5].copy()
+        out[name + "/f_est"] = recs[:, 6:10].copy()
+        out[name + "/sha"] = np.frombuffer(hashlib.sha256(iq.tobytes()).digest(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, "golden_fsk.npz"), **out)
+    dj = {}
+    for name in DFT_CASES:
+        iq = dft_input(name)
+        rc, dets = po.ref_cli_dft_detect(iq, 48000, 15.0, True, True)
+        dj[name] = {"exit_code": rc, "dets": dets, "sha": hashlib.sha256(iq.tobytes()).hexdigest()}
+    json.dump(dj, open(os.path.join(HERE, "golden_dft.json"), "w"), indent=1)
+    print("wrote golden_fsk.npz, golden_dft.json")
+
+
+if __name__ == "__main__":
+    main()

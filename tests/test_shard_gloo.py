@@ -1,0 +1,63 @@
+"""N>1 host logic on CPU: world_size-2 gloo processes scatter a shared capture by channel, each rank demodulates its
+shard (here with the oracle standing in for the GPU), counters are gathered and must equal the single-process run."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from radiosonde_auto_rx_b200 import shard
+
+
+def test_shard_range_partitions_exactly():
+    for n in (1, 7, 256, 1024, 1025):
+        for w in (1, 2, 3, 8):
+            rs = [shard.shard_range(n, w, r) for r in range(w)]
+            assert rs[0][0] == 0 and rs[-1][1] == n
+            assert all(rs[i][1] == rs[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in rs]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _worker(rank, world, port, nchan, nsamp, q):
+    import torch.distributed as dist
+    from oracle import pyoracle as po
+    from radiosonde_auto_rx_b200 import siggen
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    iq = siggen.fsk_batch(4242, nchan, nsamp, workers=2) if rank == 0 else None
+    mine = shard.scatter_capture(iq, nchan, nsamp, src=0).numpy()
+    lo, hi = shard.shard_range(nchan, world, rank)
+    assert mine.shape[0] == hi - lo
+    frames, sums = [], []
+    for c in range(hi - lo):
+        out, cons, recs = po.Oracle(po.RS41).run_stream(mine[c])
+        frames.append(len(recs))
+        sums.append(int(np.frombuffer(out.tobytes(), dtype=np.uint32).astype(np.uint64).sum() % (1 << 62)))
+    f_all = shard.gather_counts(frames, nchan)
+    s_all = shard.gather_counts(sums, nchan)
+    if rank == 0:
+        q.put((f_all.tolist(), s_all.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_scatter_shard_gather_world2(built):
+    import torch.multiprocessing as mp
+    from oracle import pyoracle as po
+    from radiosonde_auto_rx_b200 import siggen
+    nchan, nsamp, world = 5, 20_000, 2
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_worker, args=(r, world, port, nchan, nsamp, q)) for r in range(world)]
+    [p.start() for p in ps]
+    f_all, s_all = q.get(timeout=120)
+    [p.join(60) for p in ps]
+    assert all(p.exitcode == 0 for p in ps)
+    iq = siggen.fsk_batch(4242, nchan, nsamp, workers=2)
+    for c in range(nchan):
+        out, _, recs = po.Oracle(po.RS41).run_stream(iq[c])
+        assert f_all[c] == len(recs)
+        assert s_all[c] == int(np.frombuffer(out.tobytes(), dtype=np.uint32).astype(np.uint64).sum() % (1 << 62))
