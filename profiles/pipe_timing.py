@@ -22,7 +22,7 @@ per = buf.astype(float) / frames[:, None]
 m = per.mean(0)
 print(f"nchan={nchan} nsamp={nsamp} frames/ch={frames.mean():.1f} kernel_ms={b.last_kernel_ms():.3f} "
       f"=> {b.last_kernel_ms()*1e-3*1.965e9/frames.mean():.0f} cycles/frame")
-print(f"  OSC : wait est {m[0]:8.0f}  wait ring {m[1]:8.0f}  wait publish {m[2]:8.0f}  total {m[3]:8.0f}")
+print(f"  OSC : wait est {m[0]:8.0f}  wait ring {m[1]:8.0f}  recurrence {m[2]:8.0f} ({m[2]/3000:.1f} cyc/step)  total {m[3]:8.0f}")
 print(f"  CONS: wait pub/decide {m[4]:8.0f}  wait osc {m[5]:8.0f}  total {m[6]:8.0f}")
 print(f"  CTRL: wait fint {m[7]:8.0f}  total {m[8]:8.0f}")
 print(f"  EST : wait publish {m[11]:8.0f}  load {m[12]:8.0f}  fft+mag {m[13]:8.0f}  barriers+IIR {m[14]:8.0f}  total {m[15]:8.0f}")

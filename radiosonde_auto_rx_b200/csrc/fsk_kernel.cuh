@@ -156,6 +156,59 @@ __device__ __forceinline__ void warp_fft(float2 *F, const float2 *tw, const FskK
     }
 }
 
+/* The same FFT on NB independent buffers at once: the butterflies of different buffers are independent, so their
+ * shared-memory loads and FP32 chains overlap (one warp per FFT is latency-bound: ~10 cycles per instruction). */
+template <bool PAD, int NB>
+__device__ __forceinline__ void warp_fft_multi(float2 *const (&F)[NB], const float2 *tw, const FskKParams &p, int lane)
+{
+    const int lgn = 31 - __clz(p.Ndft);
+#pragma unroll 1
+    for (int st = p.nstage - 1; st >= 0; --st) {
+        const int radix = p.radix[st], lm = p.log2m[st], m = 1 << lm, fs = p.fstride[st];
+        const int lr = (radix == 2) ? 1 : 2;
+        const int nb = 1 << (lgn - lr);
+#pragma unroll 1
+        for (int b = lane; b < nb; b += 32) {
+            const int blk = b >> lm, u = b & (m - 1);
+            const int i0 = (blk << (lm + lr)) + u;
+            if (radix == 2) {
+                const int a0 = fpad<PAD>(i0), a1 = fpad<PAD>(i0 + m);
+                const float2 w = tw[fs * u];
+                float2 x0[NB], x1[NB];
+#pragma unroll
+                for (int q = 0; q < NB; ++q) { x0[q] = F[q][a0]; x1[q] = F[q][a1]; }
+#pragma unroll
+                for (int q = 0; q < NB; ++q) {
+                    const float2 t = cmul_rn(x1[q], w);
+                    F[q][a1] = csub_rn(x0[q], t);
+                    F[q][a0] = cadd_rn(x0[q], t);
+                }
+            } else {
+                const int a0 = fpad<PAD>(i0), a1 = fpad<PAD>(i0 + m), a2 = fpad<PAD>(i0 + 2 * m), a3 = fpad<PAD>(i0 + 3 * m);
+                const float2 w1 = tw[fs * u], w2 = tw[fs * u * 2], w3 = tw[fs * u * 3];
+                float2 x0[NB], x1[NB], x2[NB], x3[NB];
+#pragma unroll
+                for (int q = 0; q < NB; ++q) { x0[q] = F[q][a0]; x1[q] = F[q][a1]; x2[q] = F[q][a2]; x3[q] = F[q][a3]; }
+#pragma unroll
+                for (int q = 0; q < NB; ++q) {
+                    const float2 s0 = cmul_rn(x1[q], w1);
+                    const float2 s1 = cmul_rn(x2[q], w2);
+                    const float2 s2 = cmul_rn(x3[q], w3);
+                    const float2 s5 = csub_rn(x0[q], s1);
+                    const float2 a  = cadd_rn(x0[q], s1);
+                    const float2 s3 = cadd_rn(s0, s2);
+                    const float2 s4 = csub_rn(s0, s2);
+                    F[q][a2] = csub_rn(a, s3);
+                    F[q][a0] = cadd_rn(a, s3);
+                    F[q][a1] = make_float2(__fadd_rn(s5.x, s4.y), __fsub_rn(s5.y, s4.x));
+                    F[q][a3] = make_float2(__fsub_rn(s5.x, s4.y), __fadd_rn(s5.y, s4.x));
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 /* Tone estimate of one frame by ONE warp, from the final Sf of that frame: the peak picker (fsk.c:507-547) or
  * the mask correlator (fsk.c:566-581), whichever fsk_set_freq_est_alg selected.  Returns, for each tone, the
  * index into the host-built (cos,sin) oscillator-step LUT.  Ties resolve to the lowest bin, as the

@@ -40,14 +40,16 @@
 #define PFLUSH(base, n)
 #endif
 
-#define PIPE_THREADS 384        /* 12 warps: OSC 1, TIME 1, DEC 1, CONS 4, EST 5 */
+#define PIPE_THREADS 384        /* 12 warps: OSC 1, TIME 1, DEC 1, CONS 4, EST 4, 1 idle (keeps the oscillator's sub-partition quiet) */
 #define PIPE_R    1024          /* ring capacity per tone, samples (power of two, multiple of PIPE_BLK) */
 #define PIPE_BLK  128           /* consumer block / oscillator publication granularity                  */
-#define PIPE_NEST 5             /* EST warps  */
+#define PIPE_NEST 4             /* EST warps  */
 #define PIPE_NCONS 4            /* CONS warps */
 #define PIPE_TB   64            /* timing terms per batch */
+#define PIPE_OSC_CHUNK 256       /* oscillator steps between flow-control checks / position publications */
+#define PIPE_NFB  3             /* FFTs a warp advances together */
 
-enum { ROLE_OSC = 0, ROLE_TIME, ROLE_DEC, ROLE_CONS, ROLE_EST };
+enum { ROLE_OSC = 0, ROLE_TIME, ROLE_DEC, ROLE_CONS, ROLE_EST, ROLE_IDLE };
 
 struct PipeDesc {               /* per-frame descriptor, 4 slots */
     int    c;                   /* frame start, samples relative to this call's stream start */
@@ -70,14 +72,36 @@ __device__ __forceinline__ void st_rel(int *p, int v)
 {
     asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
-/* Warp-uniform wait: lane 0 polls `*flag >= want`, giving up when `*stop` is raised. */
-__device__ __forceinline__ bool warp_wait_ge(const int *flag, int want, const int *stop, int lane, unsigned ns = 200)
+/* Counter + doorbell.  Correctness rests on the monotonic shared-memory counters (release/acquire); the doorbell
+ * is an mbarrier (arrival count 1) the producer rings after every counter update so that a waiter can SUSPEND in
+ * hardware (mbarrier.try_wait with a time hint) instead of spinning: polling loops were 62 % of all issued
+ * instructions before (profiles/r01_notes.md).  A waiter that falls two rings behind merely sleeps one hint. */
+enum { DB_PUB = 0, DB_EST, DB_OSC, DB_FREE, DB_FINT, DB_TIME, DB_DEC, DB_COUNT };
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_ring(unsigned long long *bar)
+{
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity, unsigned hint_ns)
+{
+    unsigned ok;
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity), "r"(hint_ns) : "memory");
+    return ok != 0;
+}
+/* Warp-uniform wait for `*flag >= want` (lane 0 waits, result broadcast); gives up when `*stop` is raised. */
+__device__ __forceinline__ bool warp_wait_ge(const int *flag, int want, const int *stop, int lane,
+                                             unsigned long long *bell, unsigned &par, unsigned hint_ns = 1000)
 {
     int ok = 1;
     if (lane == 0) {
         while (ld_acq(flag) < want) {
             if (ld_acq(stop)) { ok = (ld_acq(flag) >= want); break; }
-            __nanosleep(ns);
+            if (mbar_try_wait(bell, par, hint_ns)) par ^= 1u;
         }
     }
     ok = __shfl_sync(0xffffffffu, ok, 0);
@@ -107,6 +131,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
     __shared__ int s_frames, s_nin_state, s_high_last, s_nan_last;
     __shared__ float s_nrt_state, s_ppm_state;
     __shared__ float2 s_phi0[4];
+    __shared__ unsigned long long s_bell[DB_COUNT];
 
     const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int Ndft = p.Ndft, Nmem = p.Nmem, nfi = p.nfi, P = p.P, Ts = p.Ts, nsym = p.Nsym;
@@ -149,6 +174,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
         const bool exists0 = nin0 <= nsamp_rel;
         desc[0].c = 0; desc[0].nin = nin0; desc[1].c = nin0;
         s_published = exists0 ? 1 : 0; s_stop = exists0 ? 0 : 1;
+        for (int i = 0; i < DB_COUNT; ++i) mbar_init(&s_bell[i], 1);
     }
     __syncthreads();
 
@@ -157,19 +183,19 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
        two oscillators sit on different sub-partitions. */
     const int rw = (warp + 12 - (blockIdx.x >= 148 ? 1 : 0)) % 12;
     int role, ridx;                                                     /* ridx: index inside the role's group */
-    switch (rw) {      /* sub-partition 0: OSC, DEC, TIME | 1: CONS x3 | 2: EST x3 | 3: EST x2, CONS */
+    switch (rw) {      /* sub-partition 0: OSC, DEC (light), one idle warp | 1: TIME, CONS, CONS | 2: CONS, EST, EST | 3: CONS, EST, EST */
         case 0: role = ROLE_OSC; ridx = 0; break;
         case 4: role = ROLE_DEC; ridx = 0; break;
-        case 8: role = ROLE_TIME; ridx = 0; break;
-        case 1: role = ROLE_CONS; ridx = 0; break;
-        case 5: role = ROLE_CONS; ridx = 1; break;
-        case 9: role = ROLE_CONS; ridx = 2; break;
+        case 8: role = ROLE_IDLE; ridx = 0; break;
+        case 1: role = ROLE_TIME; ridx = 0; break;
+        case 5: role = ROLE_CONS; ridx = 0; break;
+        case 9: role = ROLE_CONS; ridx = 1; break;
+        case 2: role = ROLE_CONS; ridx = 2; break;
         case 3: role = ROLE_CONS; ridx = 3; break;
-        case 2: role = ROLE_EST; ridx = 0; break;
-        case 6: role = ROLE_EST; ridx = 1; break;
-        case 10: role = ROLE_EST; ridx = 2; break;
-        case 7: role = ROLE_EST; ridx = 3; break;
-        default: role = ROLE_EST; ridx = 4; break;     /* rw == 11 */
+        case 6: role = ROLE_EST; ridx = 0; break;
+        case 10: role = ROLE_EST; ridx = 1; break;
+        case 7: role = ROLE_EST; ridx = 2; break;
+        default: role = ROLE_EST; ridx = 3; break;     /* rw == 11 */
     }
     unsigned char *outb = (unsigned char *)p.out + (long long)c * p.out_stride * (p.soft ? 4 : 1);
 
@@ -178,23 +204,25 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
         float2 ph = lane < M ? s_phi0[lane] : make_float2(1.0f, 0.0f);
         float2 *myring = ring + (lane < M ? lane : 0) * PIPE_R;
         int pos = 0;
+        unsigned par_est = 0, par_free = 0, par_pub = 0;
         PDECL
         for (int k = 0;; ++k) {
-            { PTIC const bool ok_ = warp_wait_ge(&s_est_done, k + 1, &s_stop, lane); PTOC(0); if (!ok_) break; }
+            { PTIC const bool ok_ = warp_wait_ge(&s_est_done, k + 1, &s_stop, lane, &s_bell[DB_EST], par_est); PTOC(0); if (!ok_) break; }
             const float2 d = desc[k & 3].dphi[lane < M ? lane : 0];
             int done = 0, target = nin_min, nin = -1;
             bool stopped = false;
             while (true) {
                 while (done < target) {
-                    const int n = min(PIPE_BLK - (pos & (PIPE_BLK - 1)), target - done);
+                    const int n = min(PIPE_OSC_CHUNK - (pos & (PIPE_OSC_CHUNK - 1)), target - done);
                     int ok = 1;
                     PTIC
                     if (lane == 0) {                                     /* ring space: slot of pos+n-1 must be free */
-                        while (pos + n - ld_acq(&s_free_pos) > PIPE_R) { if (ld_acq(&s_stop)) { ok = 0; break; } __nanosleep(100); }
+                        while (pos + n - ld_acq(&s_free_pos) > PIPE_R) { if (ld_acq(&s_stop)) { ok = 0; break; } if (mbar_try_wait(&s_bell[DB_FREE], par_free, 1000)) par_free ^= 1u; }
                     }
                     ok = __shfl_sync(0xffffffffu, ok, 0);
                     PTOC(1);
                     if (!ok) { stopped = true; break; }
+                    { PTIC
                     if (lane < M) {
                         float2 *dst = myring + (pos & (PIPE_R - 1));
                         int j = 0;
@@ -205,11 +233,12 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
                         if (j < n) { ph = cmul_rn(ph, d); dst[j] = ph; }
                     }
                     __syncwarp();
+                    PTOC(3); }
                     pos += n; done += n;
-                    if (lane == 0) st_rel(&s_osc_pos, pos);
+                    if (lane == 0) { st_rel(&s_osc_pos, pos); mbar_ring(&s_bell[DB_OSC]); }
                 }
                 if (stopped || nin >= 0) break;
-                { PTIC const bool ok_ = warp_wait_ge(&s_published, k + 1, &s_stop, lane); PTOC(2); if (!ok_) { stopped = true; break; } }
+                { PTIC const bool ok_ = warp_wait_ge(&s_published, k + 1, &s_stop, lane, &s_bell[DB_PUB], par_pub); PTOC(2); if (!ok_) { stopped = true; break; } }
                 nin = desc[k & 3].nin; target = nin;
             }
             if (stopped) break;
@@ -220,12 +249,16 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
             }
             __syncwarp();
         }
+#ifdef FSK_PROFILE
+        pacc[2] = pacc[3];   /* report pure recurrence cycles in the 'wait publish' slot */
+#endif
         PFLUSH(0, 3);
     } else if (role == ROLE_TIME) {
         /* =========================== TIME: fine timing, publish next frame ========================== */
         float nrt_state = s_nrt_state, ppm = s_ppm_state;
         int k = 0;
         bool exists = ld_acq(&s_published) >= 1;
+        unsigned par_fint = 0;
         PDECL
         while (exists) {
             const int ck = desc[k & 3].c, nin = desc[k & 3].nin;
@@ -234,7 +267,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
             float2 pf0 = __ldg(p.phi_ft + min(lane, nfi - 1)), pf1 = __ldg(p.phi_ft + min(lane + 32, nfi - 1));
             for (int i0 = 0; i0 < nfi; i0 += PIPE_TB) {                  /* fsk.c:686-698, streamed */
                 const int cnt = min(PIPE_TB, nfi - i0);
-                { PTIC warp_wait_ge(&s_fint_total, k * nfi + i0 + cnt, &s_stop, lane, 100); PTOC(0); }
+                { PTIC warp_wait_ge(&s_fint_total, k * nfi + i0 + cnt, &s_stop, lane, &s_bell[DB_FINT], par_fint); PTOC(0); }
                 const float2 q0 = pf0, q1 = pf1;
                 if (i0 + PIPE_TB < nfi) {                                /* prefetch the next batch's table entries */
                     pf0 = __ldg(p.phi_ft + min(i0 + PIPE_TB + lane, nfi - 1));
@@ -280,11 +313,11 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
             const bool exists_next = (p.max_frames <= 0 || k + 1 < p.max_frames) && (c_next + nin_next <= nsamp_rel);
             if (lane == 0) {
                 s_nin_state = nin_next; s_nrt_state = nrt_state; s_ppm_state = ppm; s_high_last = high; s_nan_last = nan;
-                if (exists_next) { desc[(k + 1) & 3].nin = nin_next; desc[(k + 2) & 3].c = c_next + nin_next; st_rel(&s_published, k + 2); }
+                if (exists_next) { desc[(k + 1) & 3].nin = nin_next; desc[(k + 2) & 3].c = c_next + nin_next; st_rel(&s_published, k + 2); mbar_ring(&s_bell[DB_PUB]); }
                 PipeDesc &dk = desc[k & 3];
                 dk.nan = nan; dk.low = low; dk.high = high; dk.nin_next = nin_next; dk.exists_next = exists_next ? 1 : 0;
                 dk.fract = fract; dk.nrt = nrt_state; dk.ppm = ppm;
-                st_rel(&s_time_done, k + 1);
+                st_rel(&s_time_done, k + 1); mbar_ring(&s_bell[DB_TIME]);
             }
             __syncwarp();
             exists = exists_next; ++k;
@@ -292,8 +325,9 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
         PFLUSH(7, 1);
     } else if (role == ROLE_DEC) {
         /* =========================== DEC: decisions, outputs, EbNo sums, frame record ================ */
+        unsigned par_time = 0;
         for (int k = 0;; ++k) {
-            if (!warp_wait_ge(&s_time_done, k + 1, &s_stop, lane)) break;
+            if (!warp_wait_ge(&s_time_done, k + 1, &s_stop, lane, &s_bell[DB_TIME], par_time, 2000)) break;
             const PipeDesc &dk = desc[k & 3];
             const int nan = dk.nan, low = dk.low, high = dk.high, nin = dk.nin, exists_next = dk.exists_next;
             const float fract = dk.fract;
@@ -358,8 +392,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
                 }
                 s_frames = k + 1;
                 __threadfence_block();
-                st_rel(&s_decide_done, k + 1);
-                if (!exists_next) st_rel(&s_stop, 1);
+                st_rel(&s_decide_done, k + 1); mbar_ring(&s_bell[DB_DEC]);
+                if (!exists_next) { st_rel(&s_stop, 1); for (int i = 0; i < DB_COUNT; ++i) mbar_ring(&s_bell[i]); }   /* wake every sleeper */
             }
             __syncwarp();
             if (!exists_next) break;
@@ -367,9 +401,10 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
     } else if (role == ROLE_CONS) {
         /* =========================== CONS: down-convert + integrate, streaming ===================== */
         const int ct = ridx * 32 + lane, NCT = PIPE_NCONS * 32;
+        unsigned par_pub = 0, par_dec = 0, par_osc = 0;
         PDECL
         for (int k = 0;; ++k) {
-            { PTIC const bool ok_ = warp_wait_ge(&s_published, k + 1, &s_stop, lane) && warp_wait_ge(&s_decide_done, k - 1, &s_stop, lane); PTOC(0); if (!ok_) break; }
+            { PTIC const bool ok_ = warp_wait_ge(&s_published, k + 1, &s_stop, lane, &s_bell[DB_PUB], par_pub, 2000) && warp_wait_ge(&s_decide_done, k - 1, &s_stop, lane, &s_bell[DB_DEC], par_dec, 2000); PTOC(0); if (!ok_) break; }
             const int ck = desc[k & 3].c, nin = desc[k & 3].nin, base = ck + nin - Nmem, fend = ck + nin;
             float2 *fint = fintb + (size_t)(k & 1) * M * nfi;
             int i_done = 0;
@@ -379,7 +414,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
                 const int cnt = min(PIPE_BLK, fend - s0);
                 const float2 xv = xn;
                 if (s0 + PIPE_BLK + ct < fend) xn = load_sample_t<FMT>(p.in, gbase + s0 + PIPE_BLK + ct);   /* prefetch next block */
-                { PTIC warp_wait_ge(&s_osc_pos, s0 + cnt, &s_stop, lane, 100); PTOC(1); }   /* a published frame is always completed by OSC */
+                { PTIC warp_wait_ge(&s_osc_pos, s0 + cnt, &s_stop, lane, &s_bell[DB_OSC], par_osc); PTOC(1); }   /* a published frame is always completed by OSC */
                 if (ct < cnt) {
                     const int slot = (s0 + ct) & (PIPE_R - 1);
                     for (int m = 0; m < M; ++m) {
@@ -402,51 +437,66 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
                 }
                 group_bar(2, NCT);
                 if (ct == 0) {
-                    st_rel(&s_fint_total, k * nfi + i_hi);
-                    st_rel(&s_free_pos, min(base + i_hi * step, fend - p.tailcap));
+                    st_rel(&s_fint_total, k * nfi + i_hi); mbar_ring(&s_bell[DB_FINT]);
+                    st_rel(&s_free_pos, min(base + i_hi * step, fend - p.tailcap)); mbar_ring(&s_bell[DB_FREE]);
                 }
                 i_done = i_hi;
             }
         }
         if (ridx == 0) PFLUSH(4, 2);
-    } else {
+    } else if (role == ROLE_EST) {
         /* =========================== EST: FFTs -> Sf -> tone estimate, one frame ahead =============== */
         const int ew = ridx;
         const int et = ew * 32 + lane, NET = PIPE_NEST * 32;
         const int numffts = (int)floorf(__fdiv_rn((float)nin_min, (float)(Ndft / 2))) - 1;   /* same for all 3 nin (host-checked) */
-        float2 *F = fftbuf + ew * (Ndft + (Ndft >> 3));                  /* padded: i -> i + i/8 */
+        float2 *F = fftbuf + ew * PIPE_NFB * (Ndft + (Ndft >> 3));       /* PIPE_NFB padded buffers: i -> i + i/8 */
+        unsigned par_pub = 0;
         const int npl = (Ndft + 31) >> 5;                                /* samples per lane per window (<= 8: Ndft <= 256) */
         PDECL
         for (int k = 0;; ++k) {
-            { PTIC const bool ok_ = warp_wait_ge(&s_published, k, &s_stop, lane); PTOC(0); if (!ok_) break; }
+            { PTIC const bool ok_ = warp_wait_ge(&s_published, k, &s_stop, lane, &s_bell[DB_PUB], par_pub, 2000); PTOC(0); if (!ok_) break; }
             const int ck = desc[k & 3].c;
             if (!(ck + nin_min <= nsamp_rel && (p.max_frames <= 0 || k < p.max_frames))) break;   /* frame k cannot exist */
             const float *Sf_in = Sfbuf + ((k + 1) & 1) * Ndft;
             float *Sf_out = Sfbuf + (k & 1) * Ndft;
-            /* this warp's windows: j = ew, ew+NEST, ...; the next window's samples are fetched while the current FFT runs */
-            float2 v[8];
-            { PTIC
-            if (ew < numffts) {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) { const int i = q * 32 + lane; if (q < npl && i < Ndft) v[q] = load_sample_t<FMT>(p.in, gbase + ck + ew * (Ndft / 2) + i); }
-            }
-            PTOC(1); }
-            for (int j = ew; j < numffts; j += PIPE_NEST) {
+            /* this warp's windows: j = ew, ew+NEST, ... taken PIPE_NFB at a time so that the loads, butterflies and
+               magnitudes of independent FFTs overlap (fsk.c:466-503) */
+            for (int j0 = ew; j0 < numffts; j0 += PIPE_NEST * PIPE_NFB) {
+                float2 *Fq[PIPE_NFB];
                 { PTIC
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {                            /* fsk.c:470-478: window, scatter to DIT order */
-                    const int i = q * 32 + lane;
-                    if (q < npl && i < Ndft) { const float h = s_hann[i]; F[fpad<true>(s_iperm[i])] = make_float2(__fmul_rn(h, v[q].x), __fmul_rn(h, v[q].y)); }
-                }
-                if (j + PIPE_NEST < numffts) {
+                for (int g = 0; g < PIPE_NFB; ++g) Fq[g] = F + g * (Ndft + (Ndft >> 3));
+#pragma unroll 1
+                for (int ib = 0; ib < Ndft; ib += 128) {                /* 128 samples of each window per pass: 4 loads per lane per FFT in flight */
+                    float2 v[PIPE_NFB][4];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) { const int i = q * 32 + lane; if (q < npl && i < Ndft) v[q] = load_sample_t<FMT>(p.in, gbase + ck + (j + PIPE_NEST) * (Ndft / 2) + i); }
+                    for (int g = 0; g < PIPE_NFB; ++g) {
+                        const int j = j0 + g * PIPE_NEST;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int i = ib + q * 32 + lane;
+                            v[g][q] = (j < numffts && i < Ndft) ? load_sample_t<FMT>(p.in, gbase + ck + j * (Ndft / 2) + i) : make_float2(0.0f, 0.0f);
+                        }
+                    }
+#pragma unroll
+                    for (int g = 0; g < PIPE_NFB; ++g) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {                    /* fsk.c:470-478: window, scatter to DIT order */
+                            const int i = ib + q * 32 + lane;
+                            if (i < Ndft) { const float h = s_hann[i]; Fq[g][fpad<true>(s_iperm[i])] = make_float2(__fmul_rn(h, v[g][q].x), __fmul_rn(h, v[g][q].y)); }
+                        }
+                    }
                 }
                 __syncwarp();
                 PTOC(1); }
                 { PTIC
-                warp_fft<true>(F, s_tw, p, lane);
-                for (int i = lane; i < Ndft; i += 32) magbuf[j * Ndft + i] = __fsqrt_rn(mag2_rn(F[fpad<true>(i)]));
+                warp_fft_multi<true, PIPE_NFB>(Fq, s_tw, p, lane);
+#pragma unroll
+                for (int g = 0; g < PIPE_NFB; ++g) {
+                    const int j = j0 + g * PIPE_NEST;
+                    if (j < numffts)
+                        for (int i = lane; i < Ndft; i += 32) magbuf[j * Ndft + i] = __fsqrt_rn(mag2_rn(Fq[g][fpad<true>(i)]));
+                }
                 __syncwarp();
                 PTOC(2); }
             }
@@ -467,7 +517,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
                 estimate_tones(p, Sf_out, scr, s_mask, lane, tabidx);
                 if (lane < M) { const int ti = tabidx[lane]; desc[k & 3].tabidx[lane] = ti; desc[k & 3].dphi[lane] = __ldg(p.dphi_tab + ti); }
                 __syncwarp();
-                if (lane == 0) st_rel(&s_est_done, k + 1);
+                if (lane == 0) { st_rel(&s_est_done, k + 1); mbar_ring(&s_bell[DB_EST]); }
             }
         }
         if (ew == 0) PFLUSH(11, 4);
