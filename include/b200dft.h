@@ -36,7 +36,7 @@ extern "C" {
 #define B200DFT_FMT_CU8  2    /* uint8 I,Q  (u-128)/128 (dft_detect.c:573-577) */
 
 #define B200DFT_NHDR 18       /* rows of rs_hdr[] (dft_detect.c:177-194) */
-#define B200DFT_MAXDET 16     /* detections kept per channel */
+#define B200DFT_MAXDET 64     /* detections kept per channel */
 
 typedef struct b200dft b200dft_t;
 

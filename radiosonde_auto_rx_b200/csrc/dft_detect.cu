@@ -35,8 +35,8 @@
 #define SKIP_A 11                /* C34C50:  -DNOC34C50  (scan/Makefile:1)  */
 #define SKIP_B 14                /* IMET1AB: -DNOIMET1AB (scan/Makefile:1)  */
 #define FM_GAIN 0.8
-#define CORR_THREADS 256
-#define CORR_R 8                 /* lags per thread (register tile) */
+#define CORR_THREADS 384
+#define CORR_R 16                /* outputs per thread (register tile of the sliding dot product) */
 #define FRONT_TILE 512
 
 static thread_local std::string g_err;
@@ -82,7 +82,7 @@ struct HdrDev {                  /* per active header, device side */
 };
 
 struct DftParams {
-    int nchan, nact, N, K, L, lpIQtaps, lpFMtaps, delay, opt_dc, maxcnt, nblk, navg;
+    int nchan, nact, N, K, L, lpIQtaps, lpFMtaps, tpad, delay, opt_dc, maxcnt, nblk, navg;
     long long nsamp, in_stride;
     int fmt;
     const void *iq;
@@ -92,7 +92,9 @@ struct DftParams {
     const HdrDev *hdr;           /* nact */
     float2 *avg;                 /* [nchan][navg] DC estimate valid for DC-block i */
     float *fm_filt, *fm_raw;     /* [nchan][nsamp] */
-    BlkRes *res;                 /* [nchan][nblk][nact] */
+    BlkRes *res;                 /* [nz][nblk][nact] */
+    const int *chan_list;        /* [nz] channel of grid.z entry (NULL: identity)                                   */
+    const long long *sched_off;  /* [nz] samples consumed outside the block counter before this schedule (iMet branch) */
 };
 
 /* raw sample -> float pair, the conversions of f32read_csample (dft_detect.c:561-578) */
@@ -170,9 +172,29 @@ __global__ void __launch_bounds__(FRONT_TILE) dft_front_kernel(const DftParams p
 }
 
 /* ---- K2: matched-filter correlator, one CTA per (block, header, channel) ---------------------------------- */
-__device__ __forceinline__ int pad8(int i) { return i + (i >> 3); }   /* one float of padding per 8: stride-8 threads hit distinct banks */
+__device__ __forceinline__ int padr(int i) { return i + (i >> 4); }   /* one float of padding per 16: threads 16 apart hit distinct banks */
 
 __device__ __forceinline__ float fm_at(const float *fm, long long n) { return n >= 0 ? __ldg(fm + n) : 0.0f; }
+
+/* acc[r] = sum_t x[o0 + r + t] * coef[t], r < CORR_R, t < ncoef (multiple of CORR_R); x in the padded layout, o0 a multiple of
+ * CORR_R.  The CORR_R running samples live in registers and slide: one shared-memory load (+ one broadcast coefficient)
+ * per CORR_R FMAs. */
+__device__ __forceinline__ void sliding_dot(const float *xp, int o0, const float *coef, int ncoef, float (&acc)[CORR_R])
+{
+    float xs[CORR_R];
+#pragma unroll
+    for (int r = 0; r < CORR_R; ++r) { acc[r] = 0.0f; xs[r] = xp[padr(o0) + r]; }
+    for (int t0 = 0; t0 < ncoef; t0 += CORR_R) {
+        const int nb = padr(o0 + t0 + CORR_R);
+#pragma unroll
+        for (int u = 0; u < CORR_R; ++u) {
+            const float m = coef[t0 + u];
+#pragma unroll
+            for (int r = 0; r < CORR_R; ++r) acc[r] = fmaf(xs[(u + r) & (CORR_R - 1)], m, acc[r]);
+            xs[u] = xp[nb + u];
+        }
+    }
+}
 
 /* read_bufbit (dft_detect.c:821-864): integrate-and-dump bit slicer on the un-low-passed FM stream */
 __device__ void slice_bits(const float *fm, long long mvp, float spb, float dc, int symlen, int nsym, unsigned &rcount, float &grenze,
@@ -190,70 +212,62 @@ __device__ void slice_bits(const float *fm, long long mvp, float spb, float dc, 
     }
 }
 
-__global__ void __launch_bounds__(CORR_THREADS) dft_corr_kernel(const DftParams p)
+__global__ void __launch_bounds__(CORR_THREADS, 2) dft_corr_kernel(const DftParams p)
 {
     extern __shared__ float smf[];
-    const int b = blockIdx.x, a = blockIdx.y, c = blockIdx.z, tid = threadIdx.x;
+    const int b = blockIdx.x, a = blockIdx.y, z = blockIdx.z, tid = threadIdx.x;
+    const int c = p.chan_list ? p.chan_list[z] : z;
     const HdrDev &h = p.hdr[a];
-    const int K = p.K, L = h.L, W = K + L, taps = p.lpFMtaps;
-    float *xw = smf;                                  /* [taps-1 + W]  raw window with (taps-1) samples of circular history */
-    float *xf = smf + (taps - 1 + W + 8);             /* padded: pad8(W + 16) */
-    float *mt = xf + pad8(W + 24) + 8;                /* [Lpad] match */
-    float *wl = mt + h.Lpad;                          /* [taps] FM low-pass */
-    __shared__ float red[CORR_THREADS / 32]; __shared__ int redi[CORR_THREADS / 32];
+    const int K = p.K, L = h.L, W = K + L, taps = p.lpFMtaps, tpad = p.tpad, H = tpad - 1;   /* H: history points kept before the window */
+    const int nx = H + W + 2 * CORR_R;                /* raw points incl. tile overrun */
+    float *xw = smf;                                  /* padded: xw[padr(i)] = x'[i - H]  */
+    float *xf = xw + padr(nx) + 16;                   /* padded: filtered window + overrun */
+    float *mt = xf + padr(W + h.Lpad + 2 * CORR_R) + 16;   /* [Lpad] matched filter      */
+    float *wr = mt + h.Lpad;                          /* [tpad] reversed FM low-pass taps, front-padded with zeros */
+    __shared__ float red[CORR_THREADS / 32], redv[CORR_THREADS / 32]; __shared__ int redi[CORR_THREADS / 32];
     __shared__ float s_dc, s_best; __shared__ int s_mp;
 
     const float *fm = (h.use_raw ? p.fm_raw : p.fm_filt) + (long long)c * p.nsamp;
     /* the reference triggers after n = (b+1)(K-4) samples: pos = sample_out = n-1-delay (dft_detect.c:813-816,1498) */
-    const long long n_trig = (long long)(b + 1) * (K - 4), pos = n_trig - 1 - p.delay, w0 = pos - (W - 1);
-    for (int i = tid; i < W; i += CORR_THREADS) xw[taps - 1 + i] = fm_at(fm, w0 + i);         /* :376 (ring slots never written are 0) */
+    const long long n_trig = (p.sched_off ? p.sched_off[z] : 0) + (long long)(b + 1) * (K - 4), pos = n_trig - 1 - p.delay, w0 = pos - (W - 1);
+    if (n_trig > p.nsamp) {                                                  /* this schedule has fewer blocks than the launch */
+        if (tid == 0) { BlkRes r; r.score = 0.0f; r.pos = 0; r.dc = 0.0f; r.mp = -1; r.herrs = 99; r.m10 = 0; p.res[((long long)z * p.nblk + b) * p.nact + a] = r; }
+        return;
+    }
+    for (int i = tid; i < nx; i += CORR_THREADS) xw[padr(i)] = (i >= H && i < H + W) ? fm_at(fm, w0 + i - H) : 0.0f;   /* :376 */
     for (int i = tid; i < h.Lpad; i += CORR_THREADS) mt[i] = p.match[h.match_off + i];
-    for (int i = tid; i < taps; i += CORR_THREADS) wl[i] = p.ws_lpFM[h.lpFM * taps + i];
+    for (int i = tid; i < tpad; i += CORR_THREADS) { const int k = tpad - 1 - i; wr[i] = k < taps ? p.ws_lpFM[h.lpFM * taps + k] : 0.0f; }
     __syncthreads();
     /* DC over the last 2L samples of the window (:388-391); X[0] -= N*dc*0.98 == subtract 0.98*dc from all N points */
     float dc = 0.0f;
     if (p.opt_dc) {
         float s = 0.0f;
-        for (int i = K - L + tid; i < K + L; i += CORR_THREADS) s += xw[taps - 1 + i];
+        for (int i = K - L + tid; i < K + L; i += CORR_THREADS) s += xw[padr(H + i)];
         for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if ((tid & 31) == 0) red[tid >> 5] = s;
         __syncthreads();
         if (tid == 0) { float t = 0; for (int w = 0; w < CORR_THREADS / 32; ++w) t += red[w]; s_dc = (float)((double)t / (2.0 * (double)(float)L)); }
         __syncthreads();
         dc = s_dc;
+        const float sub = (float)((double)dc * 0.98);
+        /* the points before the window are the zero padding of the N-point circular buffer, shifted by -0.98dc like everything else */
+        for (int i = tid; i < H + W; i += CORR_THREADS) xw[padr(i)] -= sub;
+        __syncthreads();
     }
-    const float sub = (float)((double)dc * 0.98);
-    /* circular history: the points before the window are the zero padding of the N-point buffer, also shifted by -0.98dc */
-    for (int i = tid; i < taps - 1 + W; i += CORR_THREADS) xw[i] = (i < taps - 1 ? 0.0f : xw[i]) - sub;
-    __syncthreads();
-    /* FM low-pass as circular convolution with the taps (X *= WS, :396): xf[n] = sum_k wl[k] x'[n-k] */
-    for (int n = tid; n < W + 16; n += CORR_THREADS) {
-        float acc = 0.0f;
-        if (n < W) {
-            const float *xp = xw + taps - 1 + n;
-#pragma unroll 8
-            for (int k = 0; k < taps; ++k) acc = fmaf(wl[k], xp[-k], acc);
-        }
-        xf[pad8(n)] = acc;                                                    /* zeros beyond the window: tile overrun reads */
+    /* FM low-pass == circular convolution with the taps (X *= WS, :396): xf[n] = sum_k wl[k] x'[n-k] = sum_t wr[t] xw[n+t] */
+    for (int n0 = tid * CORR_R; n0 < W + h.Lpad + CORR_R; n0 += CORR_THREADS * CORR_R) {
+        float acc[CORR_R];
+        if (n0 < W) sliding_dot(xw, n0, wr, tpad, acc);
+#pragma unroll
+        for (int r = 0; r < CORR_R; ++r) xf[padr(n0) + r] = (n0 + r < W) ? acc[r] : 0.0f;   /* zeros beyond the window feed tile overruns */
     }
     __syncthreads();
     /* correlation: corr[lag] = sum_t xf[lag+t]*match[t], lag = i-(L-1) in [0, K]  (Z = X*Fm, :403-404) */
     const int nlag = K + 1;
     float best = -1.0f, bestv = 0.0f; int besti = -1;
     for (int lag0 = tid * CORR_R; lag0 < nlag; lag0 += CORR_THREADS * CORR_R) {
-        float acc[CORR_R], xs[CORR_R];
-#pragma unroll
-        for (int r = 0; r < CORR_R; ++r) { acc[r] = 0.0f; xs[r] = xf[pad8(lag0 + r)]; }
-        for (int t0 = 0; t0 < h.Lpad; t0 += CORR_R) {
-            const int nb = pad8(lag0 + t0 + CORR_R);                          /* lag0+t0+8 is a multiple of 8: contiguous run of 8 */
-#pragma unroll
-            for (int u = 0; u < CORR_R; ++u) {
-                const float m = mt[t0 + u];
-#pragma unroll
-                for (int r = 0; r < CORR_R; ++r) acc[r] = fmaf(xs[(u + r) & (CORR_R - 1)], m, acc[r]);
-                xs[u] = xf[nb + u];                                           /* slide: slot u now holds sample lag0+t0+8+u */
-            }
-        }
+        float acc[CORR_R];
+        sliding_dot(xf, lag0, mt, h.Lpad, acc);
 #pragma unroll
         for (int r = 0; r < CORR_R; ++r) {
             const int lag = lag0 + r;
@@ -268,7 +282,6 @@ __global__ void __launch_bounds__(CORR_THREADS) dft_corr_kernel(const DftParams 
         const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
         if (ob > best || (ob == best && oi < besti)) { best = ob; bestv = ov; besti = oi; }
     }
-    __shared__ float redv[CORR_THREADS / 32];
     if ((tid & 31) == 0) { red[tid >> 5] = best; redv[tid >> 5] = bestv; redi[tid >> 5] = besti; }
     __syncthreads();
     if (tid == 0) {
@@ -282,7 +295,7 @@ __global__ void __launch_bounds__(CORR_THREADS) dft_corr_kernel(const DftParams 
     if (mp == L - 1 || mp == K + L - 1) r.mp = -4;                            /* Randwert, :422 */
     float nrm = 0.0f;
     if (r.mp > 0) {                                                          /* xnorm over the L filtered samples under the template (:427-429) */
-        for (int i = tid; i < L; i += CORR_THREADS) { const float v = xf[pad8(mp - i)]; nrm = fmaf(v, v, nrm); }
+        for (int i = tid; i < L; i += CORR_THREADS) { const float v = xf[padr(mp - i)]; nrm = fmaf(v, v, nrm); }
         for (int o = 16; o; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
     }
     __syncthreads();
@@ -295,10 +308,9 @@ __global__ void __launch_bounds__(CORR_THREADS) dft_corr_kernel(const DftParams 
             const long long mpos = w0 + mp - taps / 2;                        /* :425,433 */
             r.pos = (unsigned)mpos;
             if (r.score > h.thres || r.score < -h.thres) {                    /* candidate: headcmp (:866-901) */
-                const float *raw = (h.use_raw ? p.fm_raw : p.fm_filt) + (long long)c * p.nsamp;
                 unsigned char bits[96]; unsigned rc = 0; float gr = 0.0f;
                 const float hdc = p.opt_dc ? dc : 0.0f;
-                slice_bits(raw, mpos + 1 - (int)(h.hLen * h.spb), h.spb, hdc, 1, h.hLen, rc, gr, bits);
+                slice_bits(fm, mpos + 1 - (int)(h.hLen * h.spb), h.spb, hdc, 1, h.hLen, rc, gr, bits);
                 const int inv = r.score < 0;
                 int errs = 0;
                 for (int i = 0; i < h.hLen; ++i) errs += ((bits[i] ^ inv) != h.bits[i]);
@@ -308,7 +320,7 @@ __global__ void __launch_bounds__(CORR_THREADS) dft_corr_kernel(const DftParams 
                     unsigned char mb; unsigned char bit0 = inv ? 1 : 0; unsigned bytes = 0; unsigned rc2 = 0; float gr2 = 0.0f;
                     for (int q = 0; q < 16; ++q) {
                         if (q < ofs) mb = h.bits[28 + 2 * q] ^ inv;
-                        else slice_bits(raw, mpos, h.spb, hdc, 2, 1, rc2, gr2, &mb);
+                        else slice_bits(fm, mpos, h.spb, hdc, 2, 1, rc2, gr2, &mb);
                         const unsigned fb = 1u ^ (bit0 ^ mb);
                         bytes = (bytes << 1) | fb;
                         bit0 = mb;
@@ -317,8 +329,38 @@ __global__ void __launch_bounds__(CORR_THREADS) dft_corr_kernel(const DftParams 
                 }
             }
         }
-        p.res[((long long)c * p.nblk + b) * p.nact + a] = r;
+        p.res[((long long)z * p.nblk + b) * p.nact + a] = r;
     }
+}
+
+/* ---- K3: iMet AFSK power test (dft_detect.c:1542-1607): |DFT| of successive D-sample segments of the filtered FM stream, summed
+ *          over m bins around 2200 / 2400 / 800 Hz.  One CTA per pending event; one warp per bin at a time. ---------------------- */
+struct ImetEv { int c; int n; long long src; };
+__global__ void dft_imet_kernel(const DftParams p, const ImetEv *ev, int m, int b22, int b24, int b8, float *out)
+{
+    const ImetEv e = ev[blockIdx.x];
+    const float *fm = p.fm_filt + (long long)e.c * p.nsamp + e.src;
+    const int N = p.N, D = N / 2 - 3, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __shared__ float pw[3];
+    if (threadIdx.x < 3) pw[threadIdx.x] = 0.0f;
+    __syncthreads();
+    const int bins0[3] = {b22 - m / 4, b24 - m / 4, b8 - m / 4};
+    for (int s0 = 0; s0 + D <= e.n; s0 += D) {
+        for (int t = warp; t < 3 * m; t += nw) {
+            const int g = t / m, bin = bins0[g] + (t - g * m);
+            float re = 0.0f, im = 0.0f;
+            for (int i = lane; i < D; i += 32) {
+                const int k = (int)(((long long)bin * i) & (N - 1));             /* N is a power of two */
+                float sn, cs; sincospif(-2.0f * (float)k / (float)N, &sn, &cs);
+                const float x = __ldg(fm + s0 + i);
+                re = fmaf(x, cs, re); im = fmaf(x, sn, im);
+            }
+            for (int o = 16; o; o >>= 1) { re += __shfl_xor_sync(0xffffffffu, re, o); im += __shfl_xor_sync(0xffffffffu, im, o); }
+            if (lane == 0) atomicAdd(&pw[g], sqrtf(re * re + im * im));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) out[blockIdx.x * 3 + threadIdx.x] = pw[threadIdx.x];
 }
 
 /* =============================== host side =================================================================== */
@@ -329,7 +371,8 @@ struct b200dft {
     float spb[NRS]; int hLen[NRS], Lj[NRS];
     float *d_ws_lpIQ = 0, *d_ws_lpFM = 0, *d_match = 0; HdrDev *d_hdr = 0;
     float2 *d_avg = 0; float *d_fm_filt = 0, *d_fm_raw = 0; BlkRes *d_res = 0; void *d_iq = 0;
-    long long cap_samp = 0, cap_iq_bytes = 0; int cap_blk = 0, cap_avg = 0;
+    long long cap_samp = 0, cap_samp_run = 0, cap_iq_bytes = 0; int cap_blk = 0, cap_avg = 0;
+    int *d_list = 0; long long *d_soff = 0;
     size_t corr_smem_max = 0;
     cudaStream_t stream = 0; cudaEvent_t ev[4] = {0, 0, 0, 0};
     long launches = 0; bool timed = false;
@@ -413,7 +456,8 @@ extern "C" int b200dft_create(b200dft_t **out, int sample_rate, double bw_khz, i
         for (int i = 0; i < hd.hLen; i++) hd.bits[i] = bits[i] & 1;
         for (int i = 0; i < hd.Lpad; i++) match_all.push_back(i < Lj ? match[i] : 0.0f);
         h->hdr.push_back(hd); h->act.push_back(j);
-        size_t sm = ((size_t)(h->lpFMtaps - 1 + h->K + Lj + 8) + (size_t)(h->K + Lj + 24 + ((h->K + Lj + 24) >> 3)) + 8 + hd.Lpad + h->lpFMtaps) * 4;
+        const int tpad = (h->lpFMtaps + CORR_R - 1) / CORR_R * CORR_R, W = h->K + Lj, nx = tpad - 1 + W + 2 * CORR_R, nf = W + hd.Lpad + 2 * CORR_R;
+        size_t sm = ((size_t)(nx + (nx >> 4) + 16) + (size_t)(nf + (nf >> 4) + 16) + hd.Lpad + tpad + 64) * 4;
         if (sm > h->corr_smem_max) h->corr_smem_max = sm;
     }
     h->nact = (int)h->hdr.size();
@@ -437,7 +481,7 @@ extern "C" void b200dft_destroy(b200dft_t *h)
 {
     if (!h) return;
     cudaSetDevice(h->device); cudaDeviceSynchronize();
-    void *ptrs[] = {h->d_ws_lpIQ, h->d_ws_lpFM, h->d_match, h->d_hdr, h->d_avg, h->d_fm_filt, h->d_fm_raw, h->d_res, h->d_iq};
+    void *ptrs[] = {h->d_ws_lpIQ, h->d_ws_lpFM, h->d_match, h->d_hdr, h->d_avg, h->d_fm_filt, h->d_fm_raw, h->d_res, h->d_iq, h->d_list, h->d_soff};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < 4; i++) cudaEventDestroy(h->ev[i]);
     cudaStreamDestroy(h->stream);
@@ -452,66 +496,116 @@ extern "C" int b200dft_info(const b200dft_t *h, b200dft_info_t *info)
     return B200DFT_OK;
 }
 
-/* The decision loop of main() (dft_detect.c:1498-1652) over the per-block records of one channel. */
-static void decide_channel(const b200dft *h, const BlkRes *res, int nblk, long nsamp_eff, int opt_cont, b200dft_result_t *out)
-{
-    const int nact = h->nact;
+/* Per-channel state of the decision loop of main() (dft_detect.c:1498-1652), resumable because the iMet AFSK branch
+ * (:1542-1607) swallows one extra second of samples OUTSIDE the block counter and so shifts every later block. */
+struct ChanRun {
     float mv[NRS]; unsigned mv_pos[NRS], mv0_pos[NRS]; int mp[NRS]; float dcv[NRS], dfv[NRS];
     const char *type[NRS]; int tn[NRS];
-    for (int j = 0; j < NRS; j++) { mv[j] = 0; mv_pos[j] = 0; mp[j] = 0; dcv[j] = dfv[j] = 0; type[j] = HDR[j].type; tn[j] = HDR[j].tn; }
-    int j_max = 0; float mv_max = 0; int header_found = 0; unsigned frm2 = 0;
-    memset(out, 0, sizeof *out);
-    (void)nsamp_eff;
-    for (int b = 0; b < nblk; b++) {
-        const BlkRes *rb = res + (size_t)b * nact;
-        for (int a = 0; a < nact; a++) {
-            const int j = h->act[a];
-            mv0_pos[j] = mv_pos[j];
-            mp[j] = rb[a].mp; dcv[j] = rb[a].dc;
-            if (rb[a].mp > 0) { mv[j] = rb[a].score; mv_pos[j] = rb[a].pos; }          /* getCorrDFT leaves them untouched on failure */
-            if (h->opt_dc) dfv[j] = dcv[j] / (2.0 * FM_GAIN * 1);
+    int j_max; float mv_max; unsigned frm2;
+    long long off;            /* samples consumed outside the block counter so far */
+    int b;                    /* next block of the current schedule */
+    bool done, need;
+    bool wait_imet; long long imet_ntrig; int imet_n, imet_hf;   /* an iMet candidate waits for its power test */
+    b200dft_result_t *out;
+};
+
+static void chan_init(ChanRun &s, b200dft_result_t *out)
+{
+    memset(&s, 0, sizeof s);
+    for (int j = 0; j < NRS; j++) { s.type[j] = HDR[j].type; s.tn[j] = HDR[j].tn; }
+    s.out = out; memset(out, 0, sizeof *out);
+}
+static void chan_finish(ChanRun &s)
+{
+    int hf; if (s.mv_max) hf = (s.mv_max < 0 && s.j_max < 3) ? -1 : 1; else hf = 0;
+    s.out->exit_code = hf * s.tn[s.j_max]; s.done = true; s.need = false;
+}
+static void chan_report(const b200dft *h, ChanRun &s, int j)                 /* the printf block, :1611-1642 */
+{
+    if (s.mv[j] > HDR[j].thres || s.mv[j] < -HDR[j].thres) {
+        if (s.out->ndet < B200DFT_MAXDET) {
+            b200dft_det_t *d = &s.out->dets[s.out->ndet];
+            d->hdr = j; d->tn = s.tn[j]; d->score = s.mv[j]; d->pos = s.mv_pos[j]; d->df_hz = s.dfv[j] * h->sr; d->m10 = s.frm2 & 0xFFFF;
+            memset(d->type, 0, sizeof d->type); strncpy(d->type, s.type[j], sizeof d->type - 1);
         }
-        header_found = 0;
+        s.out->ndet++;
+        if (j == 6) s.frm2 = 0;
+    }
+    if (fabsf(s.mv_max) < fabsf(s.mv[j])) { s.mv_max = s.mv[j]; s.j_max = j; }
+}
+
+/* Closing part of one block iteration (dft_detect.c:1649-1651) */
+static void chan_end_block(b200dft *h, ChanRun &s, int header_found, bool imet_event, int opt_cont)
+{
+    if (header_found && !opt_cont) { chan_finish(s); return; }
+    for (int j = 0; j < NRS; j++) s.mv[j] = 0.0f;
+    if (imet_event) { s.off += (long long)s.b * (h->K - 4); s.b = 0; s.need = true; }   /* later blocks follow a shifted schedule */
+}
+
+/* The iMet branch once the power sums are known (dft_detect.c:1570-1607). verdict: 1 relabel to IMET4/IMET1RS, 0 drop, -1 goto ende */
+static void chan_resume_imet(b200dft *h, ChanRun &s, int verdict, int opt_cont)
+{
+    const int j0 = IDX_IMETAFSK;
+    int header_found = s.imet_hf;
+    s.wait_imet = false;
+    s.off += s.imet_n;
+    if (verdict < 0) { chan_finish(s); return; }
+    s.mv[j0] = fabsf(s.mv[j0]);
+    if (verdict == 1) {
+        const int j = (h->bw_khz * 1e3 > 50e3) ? IDX_RS : IDX_I4;
+        s.mv[j] = s.mv[j0]; s.mv_pos[j] = s.mv_pos[j0]; s.dcv[j] = s.dcv[j0]; s.dfv[j] = s.dfv[j0]; s.mv[j0] = 0.0f;
+        header_found = 1;
+        chan_report(h, s, j);
+    } else s.mv[j0] = 0.0f;
+    chan_end_block(h, s, header_found, true, opt_cont);
+}
+
+/* Advance one channel over the results of its current schedule; stops at the end of the stream, at the first detection
+ * (no -c), when the schedule's results run out, or at an iMet candidate (s.wait_imet: the caller runs the power test). */
+static void chan_advance(b200dft *h, ChanRun &s, const BlkRes *res, int nblk_launch, long neff, int opt_cont)
+{
+    const int nact = h->nact, Kb = h->K - 4;
+    s.need = false;
+    while (!s.done && !s.need && !s.wait_imet) {
+        const long long n_trig = s.off + (long long)(s.b + 1) * Kb;
+        if (n_trig > neff) { chan_finish(s); return; }
+        if (s.b >= nblk_launch) { s.need = true; return; }
+        const BlkRes *rb = res + (size_t)s.b * nact;
         for (int a = 0; a < nact; a++) {
             const int j = h->act[a];
-            if (!(mp[j] > 0 && (mv[j] > HDR[j].thres || mv[j] < -HDR[j].thres))) continue;
-            if (!(mv_pos[j] > mv0_pos[j])) continue;
+            s.mv0_pos[j] = s.mv_pos[j];
+            s.mp[j] = rb[a].mp; s.dcv[j] = rb[a].dc;
+            if (rb[a].mp > 0) { s.mv[j] = rb[a].score; s.mv_pos[j] = rb[a].pos; }   /* getCorrDFT leaves them untouched on failure */
+            if (h->opt_dc) s.dfv[j] = s.dcv[j] / (2.0 * FM_GAIN * 1);
+        }
+        s.b++;
+        int header_found = 0;
+        for (int a = 0; a < nact; a++) {
+            const int j = h->act[a];
+            if (!(s.mp[j] > 0 && (s.mv[j] > HDR[j].thres || s.mv[j] < -HDR[j].thres))) continue;
+            if (!(s.mv_pos[j] > s.mv0_pos[j])) continue;
             if (!(rb[a].herrs < HDR[j].herrs)) continue;
-            if (j == 6) {                                                             /* M10 / M20 (:1526-1540) */
+            if (j == 6) {                                                       /* M10 / M20 (:1526-1540) */
                 const unsigned bytes = rb[a].m10; int hwt = 0; for (int q = 0; q < 4; q++) hwt += (bytes >> q) & 1;
-                if (hwt < 2 || (hwt == 2 && (bytes & 0xF0) == 0x20)) { type[j] = "M20"; tn[j] = 6; } else { type[j] = "M10"; tn[j] = 5; }
-                frm2 = bytes;
+                if (hwt < 2 || (hwt == 2 && (bytes & 0xF0) == 0x20)) { s.type[j] = "M20"; s.tn[j] = 6; } else { s.type[j] = "M10"; s.tn[j] = 5; }
+                s.frm2 = bytes;
             }
-            if (j == IDX_IMETAFSK) {
-                /* iMet AFSK preamble: the reference reads one more second and compares the 2200/2400/800 Hz FM-audio
-                   power to tell IMET4/IMET1RS from IMET1AB (:1542-1607).  Not implemented on the device path yet:
-                   the candidate is dropped exactly as when that test fails (mv[j] = 0). */
-                mv[j] = 0.0f;
-                continue;
+            if (j == IDX_IMETAFSK) {                                            /* always the last active header: park the channel */
+                const long long avail = neff - n_trig;
+                s.imet_n = (int)(avail < h->sr ? (avail > 0 ? avail : 0) : h->sr);   /* one more second is read outside the block counter */
+                s.imet_ntrig = n_trig; s.imet_hf = header_found; s.wait_imet = true;
+                return;
             }
             header_found = 1;
-            if (mv[j] > HDR[j].thres || mv[j] < -HDR[j].thres) {
-                if (out->ndet < B200DFT_MAXDET) {
-                    b200dft_det_t *d = &out->dets[out->ndet];
-                    d->hdr = j; d->tn = tn[j]; d->score = mv[j]; d->pos = mv_pos[j]; d->df_hz = dfv[j] * h->sr; d->m10 = frm2 & 0xFFFF;
-                    strncpy(d->type, type[j], sizeof d->type - 1);
-                }
-                out->ndet++;
-                if (j == 6) frm2 = 0;
-            }
-            if (fabsf(mv_max) < fabsf(mv[j])) { mv_max = mv[j]; j_max = j; }
+            chan_report(h, s, j);
         }
-        if (header_found && !opt_cont) break;
-        header_found = 0;
-        for (int j = 0; j < NRS; j++) mv[j] = 0.0f;
+        chan_end_block(h, s, header_found, false, opt_cont);
     }
-    if (mv_max) header_found = (mv_max < 0 && j_max < 3) ? -1 : 1; else header_found = 0;
-    out->exit_code = header_found * tn[j_max];
 }
 
 static int run_common(b200dft *h, const void *d_iq, int fmt, long in_stride, long nsamp, int opt_cont, double tl, b200dft_result_t *res)
 {
-    /* -t: the reference stops once sample_in > (tl+1)*sr, i.e. it reads floor((tl+1)*sr)+1 samples at most (:1494) */
+    /* -t: blocks only trigger while sample_in <= (tl+1)*sr (:1494) */
     long neff = nsamp;
     if (tl > 0) { const long lim = (long)floor((tl + 1) * h->sr); if (neff > lim) neff = lim; }
     const int nblk = (int)(neff / (h->K - 4));
@@ -521,10 +615,14 @@ static int run_common(b200dft *h, const void *d_iq, int fmt, long in_stride, lon
         CK(cudaMalloc(&h->d_fm_filt, (size_t)h->nchan * neff * 4)); CK(cudaMalloc(&h->d_fm_raw, (size_t)h->nchan * neff * 4));
         h->cap_samp = neff;
     }
+    h->cap_samp_run = neff;
     if (navg > h->cap_avg) { if (h->d_avg) cudaFree(h->d_avg); CK(cudaMalloc(&h->d_avg, (size_t)h->nchan * navg * sizeof(float2))); h->cap_avg = navg; }
-    if (nblk > h->cap_blk) { if (h->d_res) cudaFree(h->d_res); CK(cudaMalloc(&h->d_res, (size_t)h->nchan * nblk * h->nact * sizeof(BlkRes))); h->cap_blk = nblk; }
+    if (nblk > h->cap_blk) {
+        if (h->d_res) cudaFree(h->d_res); CK(cudaMalloc(&h->d_res, (size_t)h->nchan * nblk * h->nact * sizeof(BlkRes))); h->cap_blk = nblk;
+    }
+    if (!h->d_list) { CK(cudaMalloc(&h->d_list, sizeof(int) * h->nchan)); CK(cudaMalloc(&h->d_soff, sizeof(long long) * h->nchan)); }
     DftParams p; memset(&p, 0, sizeof p);
-    p.nchan = h->nchan; p.nact = h->nact; p.N = h->N; p.K = h->K; p.L = h->L; p.lpIQtaps = h->lpIQtaps; p.lpFMtaps = h->lpFMtaps;
+    p.nchan = h->nchan; p.nact = h->nact; p.N = h->N; p.K = h->K; p.L = h->L; p.lpIQtaps = h->lpIQtaps; p.lpFMtaps = h->lpFMtaps; p.tpad = (h->lpFMtaps + CORR_R - 1) / CORR_R * CORR_R;
     p.delay = h->delay; p.opt_dc = h->opt_dc; p.maxcnt = h->maxcnt; p.nblk = nblk; p.navg = navg; p.nsamp = neff; p.in_stride = in_stride;
     p.fmt = fmt; p.iq = d_iq; p.ws_lpIQ = h->d_ws_lpIQ; p.ws_lpFM = h->d_ws_lpFM; p.match = h->d_match; p.hdr = h->d_hdr;
     p.avg = h->d_avg; p.fm_filt = h->d_fm_filt; p.fm_raw = h->d_fm_raw; p.res = h->d_res;
@@ -550,7 +648,63 @@ static int run_common(b200dft *h, const void *d_iq, int fmt, long in_stride, lon
     if (nblk > 0) CK(cudaMemcpyAsync(hres.data(), h->d_res, hres.size() * sizeof(BlkRes), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     h->timed = true;
-    for (int c = 0; c < h->nchan; c++) decide_channel(h, hres.data() + (size_t)c * nblk * h->nact, nblk, neff, opt_cont, &res[c]);
+    std::vector<ChanRun> st(h->nchan);
+    for (int c = 0; c < h->nchan; c++) chan_init(st[c], &res[c]);
+    std::vector<int> todo(h->nchan);                 /* channels that still have a schedule to walk */
+    for (int c = 0; c < h->nchan; c++) todo[c] = c;
+    std::vector<BlkRes> r2;
+    const BlkRes *rbase = hres.data(); int nb_cur = nblk; bool identity = true;
+    const float dfb = (1 / (float)h->N) * h->sr;
+    int m_imet = 50.0 / dfb; if (m_imet < 1) m_imet = 1;
+    const bool imet_ok = !(2500 * h->N / (float)h->sr > h->N / 2);
+    while (!todo.empty()) {
+        const int nz = (int)todo.size();
+        std::vector<int> pend;
+        for (int z = 0; z < nz; z++) {
+            const int c = todo[z];
+            chan_advance(h, st[c], rbase + (size_t)(identity ? c : z) * nb_cur * h->nact, nb_cur, neff, opt_cont);
+            if (st[c].wait_imet) pend.push_back(c);
+        }
+        if (!pend.empty()) {                                                   /* iMet candidates: one small kernel decides them all */
+            const int ne = (int)pend.size();
+            std::vector<ImetEv> ev(ne); std::vector<float> pw(3 * ne);
+            for (int i = 0; i < ne; i++) { ev[i].c = pend[i]; ev[i].n = st[pend[i]].imet_n; ev[i].src = st[pend[i]].imet_ntrig - h->delay; }
+            ImetEv *d_ev = 0; float *d_pw = 0;
+            CK(cudaMalloc(&d_ev, sizeof(ImetEv) * ne)); CK(cudaMalloc(&d_pw, sizeof(float) * 3 * ne));
+            CK(cudaMemcpy(d_ev, ev.data(), sizeof(ImetEv) * ne, cudaMemcpyHostToDevice));
+            dft_imet_kernel<<<ne, 256, 0, s>>>(p, d_ev, m_imet, (int)(2200 * h->N / (float)h->sr), (int)(2400 * h->N / (float)h->sr), (int)(800 * h->N / (float)h->sr), d_pw);
+            h->launches += 1;
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(pw.data(), d_pw, sizeof(float) * 3 * ne, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            cudaFree(d_ev); cudaFree(d_pw);
+            for (int i = 0; i < ne; i++) {
+                const int verdict = !imet_ok ? -1 : ((pw[3 * i] > pw[3 * i + 1] && pw[3 * i] > pw[3 * i + 2]) ? 1 : 0);
+                chan_resume_imet(h, st[pend[i]], verdict, opt_cont);
+            }
+        }
+        /* channels whose block schedule was shifted by an iMet event: correlate again from the new offset (rare, small) */
+        std::vector<int> next;
+        for (int z = 0; z < nz; z++) if (!st[todo[z]].done && st[todo[z]].need) next.push_back(todo[z]);
+        todo.swap(next);
+        if (todo.empty()) break;
+        const int nz2 = (int)todo.size();
+        std::vector<long long> off(nz2); int nb2 = 0;
+        for (int z = 0; z < nz2; z++) { off[z] = st[todo[z]].off; const int nb = (int)((neff - off[z]) / (h->K - 4)); if (nb > nb2) nb2 = nb; }
+        if (nb2 <= 0) { for (int z = 0; z < nz2; z++) chan_finish(st[todo[z]]); break; }
+        if ((long long)nz2 * nb2 > (long long)h->nchan * h->cap_blk) return fail(B200DFT_ERANGE, "relaunch buffer");
+        CK(cudaMemcpy(h->d_list, todo.data(), sizeof(int) * nz2, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->d_soff, off.data(), sizeof(long long) * nz2, cudaMemcpyHostToDevice));
+        DftParams q = p; q.nblk = nb2; q.chan_list = h->d_list; q.sched_off = h->d_soff;
+        dim3 g2(nb2, h->nact, nz2);
+        dft_corr_kernel<<<g2, CORR_THREADS, h->corr_smem_max, s>>>(q);
+        h->launches += 1;
+        CK(cudaGetLastError());
+        r2.resize((size_t)nz2 * nb2 * h->nact);
+        CK(cudaMemcpyAsync(r2.data(), h->d_res, r2.size() * sizeof(BlkRes), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        rbase = r2.data(); nb_cur = nb2; identity = false;
+    }
     return B200DFT_OK;
 }
 

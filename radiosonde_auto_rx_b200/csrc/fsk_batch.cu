@@ -45,7 +45,9 @@ struct b200fsk {
     int *d_nframes = 0; long long *d_consumed = 0; float *d_eye = 0;
     FskFrameRec *d_recs = 0; long long rec_cap = 0;      /* per channel */
     /* push path */
-    void *d_stage = 0; long long stage_cap = 0; int stage_es = 0; int carry_cap = 0; int *d_off = 0; bool off_init = false;
+    void *d_stage[2] = {0, 0}; int cur = 0;  /* double-buffered staging: kernel t reads [cur], carries its tail into [cur^1] */
+    long long stage_cap = 0; int stage_es = 0; int carry_cap = 0; int *d_off = 0; int *d_fbase = 0;
+    cudaStream_t copy_stream = 0; cudaEvent_t ev_h2d[2] = {0, 0}, ev_k[2] = {0, 0};
     void *d_out = 0; long long out_cap = 0; int out_es = 0;
     std::vector<int> h_tail;           /* per-channel carried samples (host mirror) */
     /* stats */
@@ -253,7 +255,10 @@ extern "C" int b200fsk_create(b200fsk_t **out, const b200fsk_cfg_t *cfg, int nch
     h->snr_est.assign(nchan, 0.0f); h->EbNodB.assign(nchan, 0.0f); h->last_rec.resize(nchan); h->have_rec.assign(nchan, 0);
     h->h_tail.assign(nchan, 0); h->h_nframes.assign(nchan, 0);
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1));
+    for (int i = 0; i < 2; ++i) { CK(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming)); }
+    CK(zalloc(&h->d_fbase, nchan));
     *out = h;
     return B200FSK_OK;
 }
@@ -265,9 +270,10 @@ extern "C" void b200fsk_destroy(b200fsk_t *h)
     cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->d_invperm, h->d_hann, h->d_tw, h->d_perm, h->d_phi_ft, h->d_mask, h->d_dphi, h->d_Sf, h->d_phi, h->d_tail, h->d_nrt,
                     h->d_ppm, h->d_nin, h->d_last, h->d_totf, h->d_tots, h->d_nframes, h->d_consumed, h->d_eye, h->d_recs,
-                    h->d_stage, h->d_off, h->d_out};
+                    h->d_stage[0], h->d_stage[1], h->d_off, h->d_out, h->d_fbase};
     for (void *p : ptrs) if (p) cudaFree(p);
-    cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaStreamDestroy(h->stream);
+    cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaStreamDestroy(h->stream); cudaStreamDestroy(h->copy_stream);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(h->ev_h2d[i]); cudaEventDestroy(h->ev_k[i]); }
     delete h;
 }
 
@@ -420,48 +426,66 @@ extern "C" int b200fsk_push_host(b200fsk_t *h, const void *h_in, int fmt, long i
     int rc = flush_pending(h); if (rc) return rc;
     const int es = esize_of(fmt), nchan = h->nchan, oes = soft ? 4 : 1;
     int max_tail = 0; for (int c = 0; c < nchan; ++c) max_tail = h->h_tail[c] > max_tail ? h->h_tail[c] : max_tail;
-    if (h->d_stage && h->stage_es != es && max_tail > 0) return fail(B200FSK_EINVAL, "input format changed with samples still carried");
-    /* carry area must hold the largest tail this call can leave behind */
+    if (h->d_stage[0] && h->stage_es != es && max_tail > 0) return fail(B200FSK_EINVAL, "input format changed with samples still carried");
+    /* Long uncapped pushes are cut into time chunks so that the H2D copy of chunk t+1 overlaps the kernel of chunk t
+       (the kernel is latency-bound per channel, so chunking along time costs nothing). */
+    int nchunk = 1;
+    if (max_frames <= 0 && nsamp >= 16L * h->ncap) { nchunk = 8; while (nchunk > 1 && nsamp / nchunk < 8L * h->ncap) nchunk >>= 1; }
+    const long chunk = (nsamp + nchunk - 1) / nchunk;
     const long long need_carry = (max_frames > 0 ? (long long)max_tail + nsamp : 0) + h->ncap + 8;
-    const long long need_total = need_carry + nsamp;
-    if (!h->d_stage || h->stage_es != es || h->carry_cap < need_carry || h->stage_cap < (long long)h->carry_cap + nsamp) {
+    if (!h->d_stage[0] || h->stage_es != es || h->carry_cap < need_carry || h->stage_cap < (long long)h->carry_cap + chunk) {
         const int new_carry = (int)(need_carry > h->carry_cap ? need_carry : h->carry_cap);
-        const long long new_cap = (need_total > (long long)new_carry + nsamp ? need_total : (long long)new_carry + nsamp);
-        void *ns = 0;
-        CK(cudaMalloc(&ns, (size_t)nchan * new_cap * es));
-        if (h->d_stage && max_tail > 0)      /* move the carried tails (right-aligned before carry_cap) */
+        const long long new_cap = (long long)new_carry + chunk;
+        void *ns[2] = {0, 0};
+        CK(cudaMalloc(&ns[0], (size_t)nchan * new_cap * es)); CK(cudaMalloc(&ns[1], (size_t)nchan * new_cap * es));
+        CK(cudaDeviceSynchronize());
+        if (h->d_stage[0] && max_tail > 0)      /* move the carried tails (right-aligned before carry_cap of the current buffer) */
             for (int c = 0; c < nchan; ++c)
                 if (h->h_tail[c])
-                    CK(cudaMemcpy((char *)ns + ((size_t)c * new_cap + new_carry - h->h_tail[c]) * es,
-                                  (char *)h->d_stage + ((size_t)c * h->stage_cap + h->carry_cap - h->h_tail[c]) * es,
+                    CK(cudaMemcpy((char *)ns[h->cur] + ((size_t)c * new_cap + new_carry - h->h_tail[c]) * es,
+                                  (char *)h->d_stage[h->cur] + ((size_t)c * h->stage_cap + h->carry_cap - h->h_tail[c]) * es,
                                   (size_t)h->h_tail[c] * es, cudaMemcpyDeviceToDevice));
-        if (h->d_stage) cudaFree(h->d_stage);
-        h->d_stage = ns; h->stage_cap = new_cap; h->stage_es = es; h->carry_cap = new_carry;
-        std::vector<int> off(nchan);
-        for (int c = 0; c < nchan; ++c) off[c] = new_carry - h->h_tail[c];
-        CK(cudaMemcpy(h->d_off, off.data(), sizeof(int) * nchan, cudaMemcpyHostToDevice));
+        for (int i = 0; i < 2; ++i) { if (h->d_stage[i]) cudaFree(h->d_stage[i]); h->d_stage[i] = ns[i]; }
+        h->stage_cap = new_cap; h->stage_es = es; h->carry_cap = new_carry;
+        std::vector<int> off(2 * nchan);
+        for (int c = 0; c < nchan; ++c) off[h->cur * nchan + c] = off[(h->cur ^ 1) * nchan + c] = new_carry - h->h_tail[c];
+        CK(cudaMemcpy(h->d_off, off.data(), sizeof(int) * 2 * nchan, cudaMemcpyHostToDevice));
     }
     const long long maxf = b200fsk_push_frames_bound(h, nsamp, max_frames);
     if (out_stride < maxf * h->Nbits) return fail(B200FSK_ERANGE, "out_stride %ld < %lld", out_stride, maxf * h->Nbits);
     if (!h->d_out || h->out_es != oes || h->out_cap < maxf * h->Nbits) {
+        CK(cudaDeviceSynchronize());
         if (h->d_out) cudaFree(h->d_out);
         h->out_cap = maxf * h->Nbits + 1024; h->out_es = oes;
         CK(cudaMalloc(&h->d_out, (size_t)nchan * h->out_cap * oes));
     }
     if (h->stats_on) { rc = ensure_recs(h, maxf); if (rc) return rc; }
-    cudaStream_t s = h->stream;
-    if (nsamp > 0)
-        CK(cudaMemcpy2DAsync((char *)h->d_stage + (size_t)h->carry_cap * es, (size_t)h->stage_cap * es, h_in, (size_t)in_stride * es,
-                             (size_t)nsamp * es, nchan, cudaMemcpyHostToDevice, s));
-    FskKParams kp = h->kp;
-    kp.in = h->d_stage; kp.fmt = fmt; kp.in_stride = h->stage_cap; kp.in_off = h->d_off; kp.nsamp = (long long)h->carry_cap + nsamp;
-    kp.max_frames = max_frames; kp.carry_dst = h->d_stage; kp.carry_cap = h->carry_cap; kp.in_off_next = h->d_off;
-    kp.out = h->d_out; kp.out_stride = h->out_cap; kp.soft = soft ? 1 : 0; kp.softinv = softinv ? 1 : 0; kp.frame_base = 0;
-    kp.recs = h->d_recs; kp.rec_stride = h->rec_cap; kp.write_recs = h->stats_on;
-    rc = launch(h, kp, s, true); if (rc) return rc;
+    cudaStream_t s = h->stream, cs = h->copy_stream;
+    CK(cudaMemsetAsync(h->d_fbase, 0, sizeof(int) * nchan, s));
+    CK(cudaEventRecord(h->ev0, s));
+    for (int t = 0; t < nchunk; ++t) {
+        const long s0 = (long)t * chunk, len = (s0 + chunk <= nsamp ? chunk : (nsamp > s0 ? nsamp - s0 : 0));
+        const int b = h->cur;
+        if (len > 0) {
+            CK(cudaStreamWaitEvent(cs, h->ev_k[b], 0));            /* the kernel that last read this buffer has finished */
+            CK(cudaMemcpy2DAsync((char *)h->d_stage[b] + (size_t)h->carry_cap * es, (size_t)h->stage_cap * es,
+                                 (const char *)h_in + (size_t)s0 * es, (size_t)in_stride * es, (size_t)len * es, nchan, cudaMemcpyHostToDevice, cs));
+            CK(cudaEventRecord(h->ev_h2d[b], cs));
+            CK(cudaStreamWaitEvent(s, h->ev_h2d[b], 0));
+        }
+        FskKParams kp = h->kp;
+        kp.in = h->d_stage[b]; kp.fmt = fmt; kp.in_stride = h->stage_cap; kp.in_off = h->d_off + b * nchan; kp.nsamp = (long long)h->carry_cap + len;
+        kp.max_frames = max_frames; kp.carry_dst = h->d_stage[b ^ 1]; kp.carry_cap = h->carry_cap; kp.in_off_next = h->d_off + (b ^ 1) * nchan;
+        kp.out = h->d_out; kp.out_stride = h->out_cap; kp.soft = soft ? 1 : 0; kp.softinv = softinv ? 1 : 0; kp.frame_base = h->d_fbase;
+        kp.recs = h->d_recs; kp.rec_stride = h->rec_cap; kp.write_recs = h->stats_on;
+        rc = launch(h, kp, s, false); if (rc) return rc;
+        CK(cudaEventRecord(h->ev_k[b], s));
+        h->cur ^= 1;
+    }
+    CK(cudaEventRecord(h->ev1, s)); h->timed = true;
     CK(cudaMemcpyAsync(h->h_nframes.data(), h->d_nframes, sizeof(int) * nchan, cudaMemcpyDeviceToHost, s));
     std::vector<int> off(nchan);
-    CK(cudaMemcpyAsync(off.data(), h->d_off, sizeof(int) * nchan, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(off.data(), h->d_off + h->cur * nchan, sizeof(int) * nchan, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     int mx = 0;
     for (int c = 0; c < nchan; ++c) { h->h_tail[c] = h->carry_cap - off[c]; mx = h->h_nframes[c] > mx ? h->h_nframes[c] : mx; if (frames) frames[c] = h->h_nframes[c]; }

@@ -29,7 +29,7 @@ class _Det(C.Structure):
 
 
 class _Res(C.Structure):
-    _fields_ = [("exit_code", C.c_int), ("ndet", C.c_int), ("dets", _Det * 16)]
+    _fields_ = [("exit_code", C.c_int), ("ndet", C.c_int), ("dets", _Det * 64)]
 
 
 class _Info(C.Structure):
@@ -101,7 +101,7 @@ class DftDetectBatch:
         for c in range(self.nchan):
             r = res[c]
             dets = [Detection(r.dets[i].type.decode(), r.dets[i].score, r.dets[i].pos, r.dets[i].df_hz, r.dets[i].tn, r.dets[i].m10)
-                    for i in range(min(r.ndet, 16))]
+                    for i in range(min(r.ndet, 64))]
             out.append((r.exit_code, dets))
         return out
 

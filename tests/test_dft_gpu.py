@@ -82,3 +82,23 @@ def test_output_text_matches_reference_format(cuda):
     txt = b.format_lines(dets)
     typ, rest = txt.strip().split(":")
     assert typ == "RS41" and rest.strip().endswith("Hz") and rc == 3
+
+
+def test_imet_afsk_branch_shifts_the_block_schedule(cuda):
+    """MRZ / MEISEI style 2400-baud headers also trip the iMet AFSK preamble correlator; the reference then swallows one
+    extra second of samples outside its block counter (dft_detect.c:1542-1607), which moves every later block.  Long streams
+    must still agree detection for detection."""
+    nsamp = 1 << 18
+    chans = [siggen.fm_header_iq(9001, nsamp, "RS41", snr_db=14.0), siggen.fm_header_iq(9000, nsamp, "DFM9", snr_db=14.0),
+             siggen.fm_header_iq(9009, nsamp, "MRZ", snr_db=10.0, invert=True), siggen.noise_iq(4, nsamp),
+             siggen.fm_header_iq(9007, nsamp, "MEISEI", snr_db=14.0), siggen.fm_header_iq(9025, nsamp, "MRZ", snr_db=20.0)]
+    iq = np.stack(chans)                    # shifted channels sit at indices 2, 4, 5: the relaunch must map them back correctly
+    b = dft.DftDetectBatch(48000, 15.0, True, nchan=len(chans))
+    got = b.run(iq, cont=True)
+    shifted = 0
+    for c in range(len(chans)):
+        rc, dets, blks = po.dft_oracle_run(iq[c], 48000, 15.0, True, True, want_blocks=True)
+        compare(got[c], rc, dets[:64], f"ch{c}")
+        shifted += len(blks) < 14 * (nsamp // (b.K - 4))
+    assert shifted >= 1, "the test signal no longer exercises the iMet branch"
+    assert b.launches > 3          # at least one relaunch happened
