@@ -119,40 +119,61 @@ def run_reference(args):
 # clocks sampler
 # ---------------------------------------------------------------------------------------------------
 class Clocks:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi sampler (B200_PROFILING.md clocks line), started before the warm-up so that it is already producing
+    samples when the timed region begins; only samples whose timestamp falls inside [t0, t1] are reported."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu: int):
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                       "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
 
-    def stop(self):
+    def stop(self, t0: float, t1: float):
+        import datetime
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.p.terminate()
         try:
             out, _ = self.p.communicate(timeout=5)
         except Exception:
             self.p.kill()
             out = ""
-        sm, mx, reasons = [], None, set()
+        sm_in, sm_all, mx, reasons = [], [], None, set()
         for ln in out.strip().splitlines():
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
+            if len(f) < 10:
                 continue
             try:
-                sm.append(float(f[1])); mx = float(f[2])
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                v = float(f[2]); mx = float(f[3])
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+            sm_all.append(v)
+            if t0 - 0.02 <= ts <= t1 + 0.02:
+                sm_in.append(v)
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[6:10]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        use = sm_in if sm_in else sm_all
+        return {"sm_mhz": float(np.median(use)) if use else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm_in), "samples_total": len(sm_all)}
+
+
+def ncu_traffic(nchan: int, nsamp: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of this workload, from the committed ncu capture."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(p))
+        if t.get("channels") == nchan and t.get("nsamp") == nsamp:
+            return float(t["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
 
 
 def measured_peak():
@@ -202,19 +223,24 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = Clocks(local) if rank == 0 else None
     for _ in range(args.warmup):
         step()
     barrier()
+    if rank == 0:
+        time.sleep(0.3)                    # let the sampler reach steady state before the timed region
+    barrier()
     launches0 = b.launches
-    clocks = Clocks(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
     e0.record(stream)
     for _ in range(args.steps):
         step()
     e1.record(stream)
     barrier()
+    t_wall1 = time.time()
     ms = e0.elapsed_time(e1)
-    clk = clocks.stop() if clocks else None
+    clk = clocks.stop(t_wall0, t_wall1) if clocks else None
     frames, consumed = b.counts()
     samples_per_step = float(consumed.sum())
     launches = b.launches - launches0
@@ -269,9 +295,9 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "gpu_launches_e2e": int(e2e_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "fsk_demod_kernel", "kernel_ms": kern_ms,
+                         "traffic": args.traffic_bytes if args.traffic_bytes else ncu_traffic(nchan, nsamp), "kernel": "fsk_demod_pipe_kernel<2,1>", "kernel_ms": kern_ms,
                          "algorithmic_bytes_per_sample": BYTES_PER_SAMPLE_F32, "peak_source": peak_src,
-                         "note": "latency-bound by the per-tone oscillator recurrence (8 dependent FP32 cycles/sample/channel), see DESIGN.md"},
+                         "note": "not HBM-bound: the bit-exact per-tone oscillator recurrence (4 FMUL + 2 FADD, un-fusable, one FP32 issue per ~2 cycles per warp) caps one channel at ~1 sample per 11-14 SM cycles, i.e. 256 channels at ~36-46 Gsps = 5-6 % of this peak; see DESIGN.md 4.1 and profiles/"},
         }
         if world == 1 and not args.no_cpu_baseline:
             n, dt, cores = time_reference(iq, min(nsamp, 1 << 20), args.cpu_seconds, None)
@@ -286,7 +312,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--channels", type=int, default=256)
@@ -295,6 +321,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--traffic-bytes", type=float, default=None, help="dram bytes/launch from the committed ncu capture (profiles/)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

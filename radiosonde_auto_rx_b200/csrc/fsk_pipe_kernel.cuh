@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
     __shared__ float s_nrt_state, s_ppm_state;
     __shared__ float2 s_phi0[4];
     __shared__ unsigned long long s_bell[DB_COUNT];
+    __shared__ int s_ok_cons, s_ok_est;      /* verdict of a group's polling warp, published through the group's named barrier */
 
     const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int Ndft = p.Ndft, Nmem = p.Nmem, nfi = p.nfi, P = p.P, Ts = p.Ts, nsym = p.Nsym;
@@ -404,7 +405,15 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
         unsigned par_pub = 0, par_dec = 0, par_osc = 0;
         PDECL
         for (int k = 0;; ++k) {
-            { PTIC const bool ok_ = warp_wait_ge(&s_published, k + 1, &s_stop, lane, &s_bell[DB_PUB], par_pub, 2000) && warp_wait_ge(&s_decide_done, k - 1, &s_stop, lane, &s_bell[DB_DEC], par_dec, 2000); PTOC(0); if (!ok_) break; }
+            { PTIC
+              /* only the group's first warp polls; the others block in the named barrier (no issue slots spent) */
+              if (ridx == 0) {
+                  const bool ok_ = warp_wait_ge(&s_published, k + 1, &s_stop, lane, &s_bell[DB_PUB], par_pub, 2000) && warp_wait_ge(&s_decide_done, k - 1, &s_stop, lane, &s_bell[DB_DEC], par_dec, 2000);
+                  if (lane == 0) *(volatile int *)&s_ok_cons = ok_ ? 1 : 0;
+              }
+              group_bar(2, NCT);
+              const bool ok_ = *(volatile int *)&s_ok_cons != 0;
+              PTOC(0); if (!ok_) break; }
             const int ck = desc[k & 3].c, nin = desc[k & 3].nin, base = ck + nin - Nmem, fend = ck + nin;
             float2 *fint = fintb + (size_t)(k & 1) * M * nfi;
             int i_done = 0;
@@ -414,7 +423,10 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
                 const int cnt = min(PIPE_BLK, fend - s0);
                 const float2 xv = xn;
                 if (s0 + PIPE_BLK + ct < fend) xn = load_sample_t<FMT>(p.in, gbase + s0 + PIPE_BLK + ct);   /* prefetch next block */
-                { PTIC warp_wait_ge(&s_osc_pos, s0 + cnt, &s_stop, lane, &s_bell[DB_OSC], par_osc); PTOC(1); }   /* a published frame is always completed by OSC */
+                { PTIC
+                  if (ridx == 0) warp_wait_ge(&s_osc_pos, s0 + cnt, &s_stop, lane, &s_bell[DB_OSC], par_osc);   /* a published frame is always completed by OSC */
+                  group_bar(2, NCT);
+                  PTOC(1); }
                 if (ct < cnt) {
                     const int slot = (s0 + ct) & (PIPE_R - 1);
                     for (int m = 0; m < M; ++m) {
@@ -454,7 +466,11 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
         const int npl = (Ndft + 31) >> 5;                                /* samples per lane per window (<= 8: Ndft <= 256) */
         PDECL
         for (int k = 0;; ++k) {
-            { PTIC const bool ok_ = warp_wait_ge(&s_published, k, &s_stop, lane, &s_bell[DB_PUB], par_pub, 2000); PTOC(0); if (!ok_) break; }
+            { PTIC
+              if (ew == 0) { const bool ok_ = warp_wait_ge(&s_published, k, &s_stop, lane, &s_bell[DB_PUB], par_pub, 2000); if (lane == 0) *(volatile int *)&s_ok_est = ok_ ? 1 : 0; }
+              group_bar(1, NET);
+              const bool ok_ = *(volatile int *)&s_ok_est != 0;
+              PTOC(0); if (!ok_) break; }
             const int ck = desc[k & 3].c;
             if (!(ck + nin_min <= nsamp_rel && (p.max_frames <= 0 || k < p.max_frames))) break;   /* frame k cannot exist */
             const float *Sf_in = Sfbuf + ((k + 1) & 1) * Ndft;
