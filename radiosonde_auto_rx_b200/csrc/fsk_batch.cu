@@ -47,7 +47,7 @@ struct b200fsk {
     /* push path */
     void *d_stage[2] = {0, 0}; int cur = 0;  /* double-buffered staging: kernel t reads [cur], carries its tail into [cur^1] */
     long long stage_cap = 0; int stage_es = 0; int carry_cap = 0; int *d_off = 0; int *d_fbase = 0;
-    cudaStream_t copy_stream = 0; cudaEvent_t ev_h2d[2] = {0, 0}, ev_k[2] = {0, 0};
+    cudaStream_t copy_stream = 0, out_stream = 0; cudaEvent_t ev_h2d[2] = {0, 0}, ev_k[2] = {0, 0};
     void *d_out = 0; long long out_cap = 0; int out_es = 0;
     std::vector<int> h_tail;           /* per-channel carried samples (host mirror) */
     /* stats */
@@ -256,6 +256,7 @@ extern "C" int b200fsk_create(b200fsk_t **out, const b200fsk_cfg_t *cfg, int nch
     h->h_tail.assign(nchan, 0); h->h_nframes.assign(nchan, 0);
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1));
     for (int i = 0; i < 2; ++i) { CK(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming)); }
     CK(zalloc(&h->d_fbase, nchan));
@@ -272,7 +273,7 @@ extern "C" void b200fsk_destroy(b200fsk_t *h)
                     h->d_ppm, h->d_nin, h->d_last, h->d_totf, h->d_tots, h->d_nframes, h->d_consumed, h->d_eye, h->d_recs,
                     h->d_stage[0], h->d_stage[1], h->d_off, h->d_out, h->d_fbase};
     for (void *p : ptrs) if (p) cudaFree(p);
-    cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaStreamDestroy(h->stream); cudaStreamDestroy(h->copy_stream);
+    cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaStreamDestroy(h->stream); cudaStreamDestroy(h->copy_stream); cudaStreamDestroy(h->out_stream);
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(h->ev_h2d[i]); cudaEventDestroy(h->ev_k[i]); }
     delete h;
 }
@@ -430,7 +431,7 @@ extern "C" int b200fsk_push_host(b200fsk_t *h, const void *h_in, int fmt, long i
     /* Long uncapped pushes are cut into time chunks so that the H2D copy of chunk t+1 overlaps the kernel of chunk t
        (the kernel is latency-bound per channel, so chunking along time costs nothing). */
     int nchunk = 1;
-    if (max_frames <= 0 && nsamp >= 16L * h->ncap) { nchunk = 8; while (nchunk > 1 && nsamp / nchunk < 8L * h->ncap) nchunk >>= 1; }
+    if (max_frames <= 0 && nsamp >= 16L * h->ncap) { nchunk = 16; while (nchunk > 1 && nsamp / nchunk < 8L * h->ncap) nchunk >>= 1; }
     const long chunk = (nsamp + nchunk - 1) / nchunk;
     const long long need_carry = (max_frames > 0 ? (long long)max_tail + nsamp : 0) + h->ncap + 8;
     if (!h->d_stage[0] || h->stage_es != es || h->carry_cap < need_carry || h->stage_cap < (long long)h->carry_cap + chunk) {
@@ -463,6 +464,7 @@ extern "C" int b200fsk_push_host(b200fsk_t *h, const void *h_in, int fmt, long i
     cudaStream_t s = h->stream, cs = h->copy_stream;
     CK(cudaMemsetAsync(h->d_fbase, 0, sizeof(int) * nchan, s));
     CK(cudaEventRecord(h->ev0, s));
+    long long rows_sent = 0;
     for (int t = 0; t < nchunk; ++t) {
         const long s0 = (long)t * chunk, len = (s0 + chunk <= nsamp ? chunk : (nsamp > s0 ? nsamp - s0 : 0));
         const int b = h->cur;
@@ -481,6 +483,19 @@ extern "C" int b200fsk_push_host(b200fsk_t *h, const void *h_in, int fmt, long i
         rc = launch(h, kp, s, false); if (rc) return rc;
         CK(cudaEventRecord(h->ev_k[b], s));
         h->cur ^= 1;
+        /* every channel has, after this chunk, at least floor((samples so far - nin_max)/nin_max) whole frames: ship those rows
+           of the output now, overlapped with the following chunks (rows beyond are sent after the last kernel) */
+        if (nchunk > 1 && !h->stats_on) {
+            const long long fed = (long long)s0 + len;
+            const long long lb = fed > 2LL * h->ncap ? (fed - h->ncap) / h->ncap - 1 : 0;
+            if (lb > rows_sent) {
+                CK(cudaStreamWaitEvent(h->out_stream, h->ev_k[b], 0));
+                CK(cudaMemcpy2DAsync((char *)h_out + (size_t)rows_sent * h->Nbits * oes, (size_t)out_stride * oes,
+                                     (char *)h->d_out + (size_t)rows_sent * h->Nbits * oes, (size_t)h->out_cap * oes,
+                                     (size_t)(lb - rows_sent) * h->Nbits * oes, nchan, cudaMemcpyDeviceToHost, h->out_stream));
+                rows_sent = lb;
+            }
+        }
     }
     CK(cudaEventRecord(h->ev1, s)); h->timed = true;
     CK(cudaMemcpyAsync(h->h_nframes.data(), h->d_nframes, sizeof(int) * nchan, cudaMemcpyDeviceToHost, s));
@@ -489,9 +504,13 @@ extern "C" int b200fsk_push_host(b200fsk_t *h, const void *h_in, int fmt, long i
     CK(cudaStreamSynchronize(s));
     int mx = 0;
     for (int c = 0; c < nchan; ++c) { h->h_tail[c] = h->carry_cap - off[c]; mx = h->h_nframes[c] > mx ? h->h_nframes[c] : mx; if (frames) frames[c] = h->h_nframes[c]; }
+    if (mx > rows_sent) {
+        CK(cudaMemcpy2DAsync((char *)h_out + (size_t)rows_sent * h->Nbits * oes, (size_t)out_stride * oes,
+                             (char *)h->d_out + (size_t)rows_sent * h->Nbits * oes, (size_t)h->out_cap * oes,
+                             (size_t)(mx - rows_sent) * h->Nbits * oes, nchan, cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(h->out_stream));
     if (mx > 0) {
-        CK(cudaMemcpy2DAsync(h_out, (size_t)out_stride * oes, h->d_out, (size_t)h->out_cap * oes, (size_t)mx * h->Nbits * oes, nchan,
-                             cudaMemcpyDeviceToHost, s));
         if (h->stats_on) {
             h->h_recs.resize((size_t)nchan * mx);
             CK(cudaMemcpy2DAsync(h->h_recs.data(), (size_t)mx * sizeof(FskFrameRec), h->d_recs, (size_t)h->rec_cap * sizeof(FskFrameRec),
