@@ -464,7 +464,10 @@ extern "C" int b200dft_create(b200dft_t **out, int sample_rate, double bw_khz, i
     int maxsmem = 0;
     CK(cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     if (h->corr_smem_max + 1024 > (size_t)maxsmem) { delete h; return fail(B200DFT_EINVAL, "correlator window does not fit shared memory"); }
-    CK(cudaFuncSetAttribute(dft_corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->corr_smem_max));
+    {   /* per-function attribute: allow the device maximum (minus the kernel's static shared memory) */
+        cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, (const void *)dft_corr_kernel));
+        CK(cudaFuncSetAttribute(dft_corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsmem - (int)fa.sharedSizeBytes));
+    }
     std::vector<float> wfm(2 * h->lpFMtaps);
     for (int i = 0; i < h->lpFMtaps; i++) { wfm[i] = wfm0[i]; wfm[h->lpFMtaps + i] = wfm1[i]; }
     CK(cudaMalloc(&h->d_ws_lpIQ, wiq.size() * 4)); CK(cudaMemcpy(h->d_ws_lpIQ, wiq.data(), wiq.size() * 4, cudaMemcpyHostToDevice));

@@ -98,6 +98,16 @@ static const void *pipe_kernel_fn(int M, int fmt)
     return (const void *)tab[M == 4 ? 1 : 0][fmt & 3];
 }
 
+/* Max dynamic shared memory is a per-FUNCTION attribute: always raise it to what the device allows for that function
+   (opt-in maximum minus its static shared memory) so that handles with different working sets can coexist. */
+static cudaError_t allow_max_smem(const void *fn, int maxsmem_optin)
+{
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, fn);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsmem_optin - (int)fa.sharedSizeBytes);
+}
+
 template <class T> static cudaError_t upload(T **dptr, const std::vector<T> &v)
 {
     cudaError_t e = cudaMalloc((void **)dptr, v.size() * sizeof(T));
@@ -226,11 +236,12 @@ extern "C" int b200fsk_create(b200fsk_t **out, const b200fsk_cfg_t *cfg, int nch
     int maxsmem = 0;
     CK(cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     if (h->smem + 256 > (size_t)maxsmem) { delete h; return fail(B200FSK_ENOMEM, "frame working set %zu B exceeds shared memory %d B", h->smem, maxsmem); }
-    CK(cudaFuncSetAttribute(fsk_demod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    /* the attribute is per function, not per handle: always allow the device maximum so handles of different sizes coexist */
+    CK(allow_max_smem((const void *)fsk_demod_kernel, maxsmem));
     if (h->use_pipe) {
         for (int f = 0; f < 4; ++f) {
             const void *fn = pipe_kernel_fn(M, f);
-            CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_pipe));
+            CK(allow_max_smem(fn, maxsmem));
         }
     }
 

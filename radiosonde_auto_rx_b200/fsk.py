@@ -325,3 +325,35 @@ def fsk_get_demod_stats(fsk: FSK) -> ModemStats:                                
 def fsk_clear_estimators(fsk: FSK) -> None:                                       # fsk.c:981
     fsk._batch().clear_estimators()
     fsk._nin = fsk.N
+
+
+# ==================================================================================================
+# Mixed batches (BASELINE.json configs[3]): channels with different modem parameters
+# ==================================================================================================
+class FskMixedBatch:
+    """A set of channels with assorted (Fs, Rs, M, P, Nsym, limits, estimator) settings.  Channels that share a
+    configuration are grouped into one :class:`FskBatch` handle (one kernel launch per group and push); channel
+    order is preserved in the results.  `configs[c]` are keyword arguments of :class:`FskBatch` (without nchan)."""
+
+    def __init__(self, configs: list[dict], device: int = 0):
+        self.configs = [dict(c) for c in configs]
+        self.groups: dict[tuple, list[int]] = {}
+        for c, cfg in enumerate(self.configs):
+            self.groups.setdefault(tuple(sorted(cfg.items())), []).append(c)
+        self.batches = {k: FskBatch(**dict(k), nchan=len(ch), device=device) for k, ch in self.groups.items()}
+
+    def push(self, data: list[np.ndarray], fmt: str = "cs16", soft: bool = True, softinv: bool = False):
+        """data[c]: the new samples of channel c (channels of one group must bring equally many).  Returns per channel
+        the 1-D array of bits / soft decisions produced by this push."""
+        res: list = [None] * len(self.configs)
+        for k, ch in self.groups.items():
+            b = self.batches[k]
+            block = np.stack([np.ascontiguousarray(data[c]).reshape(-1) for c in ch])
+            out, frames = b.push(block, fmt, soft=soft, softinv=softinv)
+            for i, c in enumerate(ch):
+                res[c] = out[i, : frames[i] * b.Nbits].copy()
+        return res
+
+    def close(self):
+        for b in self.batches.values():
+            b.close()

@@ -194,3 +194,23 @@ def test_exact_math_device_equals_libm(cuda):
             assert np.float32(b.stats(0).norm_rx_timing).tobytes() == recs[k]["norm_rx_timing"].tobytes()
             k += 1
     assert k > 50
+
+
+def test_mixed_2fsk_4fsk_batch(cuda):
+    """BASELINE.json configs[3] in miniature: channels at assorted rates / orders share the GPU, each bit-exact."""
+    names = ["rs41", "rs92", "dfm_softinv", "m10", "4fsk_mask", "rs41", "meisei", "4fsk_mask", "wxr301_mask", "rs41"]
+    cfgs, data, ref = [], [], []
+    for i, n in enumerate(names):
+        cfg, kw = CONFIGS[n]
+        iq = siggen.fsk_iq(800 + i, 70_000, ebno_db=11.0, **kw)
+        cfgs.append(dict(Fs=cfg.Fs, Rs=cfg.Rs, M=cfg.M, P=cfg.P, Nsym=cfg.Nsym, f1_tx=1000, fs_tx=cfg.fs_tx, est_min=cfg.lo,
+                         est_max=cfg.hi, est_type=1 if cfg.mask else 0))
+        data.append(iq)
+        soft_cfg = po.FskConfig(cfg.Fs, cfg.Rs, cfg.M, cfg.P, cfg.Nsym, cfg.lower, cfg.upper, cfg.mask, True, False)
+        ref.append(po.Oracle(soft_cfg).run_stream(iq)[0])
+    mb = fsk.FskMixedBatch(cfgs)
+    assert len(mb.batches) == 7
+    got = mb.push(data, "cs16", soft=True)
+    for c in range(len(names)):
+        assert got[c].tobytes() == ref[c].tobytes(), names[c]
+    mb.close()
