@@ -40,11 +40,11 @@
 #define PFLUSH(base, n)
 #endif
 
-#define PIPE_THREADS 512        /* 16 warps: OSC 1, DEC 1, TIME 1, CONS 3, EST 4 and 6 idle ones that keep the oscillator sub-partitions quiet */
+#define PIPE_THREADS 384        /* 12 warps: OSC 1, TIME 1, DEC 1, CONS 4, EST 4, 1 idle (keeps the oscillator's sub-partition quiet) */
 #define PIPE_R    1024          /* ring capacity per tone, samples (power of two, multiple of PIPE_BLK) */
-#define PIPE_BLK  96            /* consumer block (= CONS threads)                                      */
+#define PIPE_BLK  128           /* consumer block / oscillator publication granularity                  */
 #define PIPE_NEST 4             /* EST warps  */
-#define PIPE_NCONS 3            /* CONS warps */
+#define PIPE_NCONS 4            /* CONS warps */
 #define PIPE_TB   64            /* timing terms per batch */
 #define PIPE_OSC_CHUNK 256       /* oscillator steps between flow-control checks / position publications */
 #define PIPE_NFB  3             /* FFTs a warp advances together */
@@ -179,24 +179,24 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
     }
     __syncthreads();
 
-    /* Warp roles.  SM sub-partition = warp id % 4.  Two CTAs (two channels) share an SM; a CTA's 16 warps form four groups of
-       four: {OSC, DEC, idle, idle}, {idle x4}, {TIME, CONS x3}, {EST x4}.  The first CTA of an SM puts them on sub-partitions
-       0,1,2,3, the second (bid >= #SMs) on 1,0,3,2 (warp id ^ 1): each oscillator then shares its sub-partition only with its own
-       light DEC warp and idle warps of both CTAs, and the two CTAs' heavy groups are paired EST-with-TIME/CONS. */
-    const int rw = warp ^ (blockIdx.x >= 148 ? 1 : 0);
+    /* Warp roles.  SM sub-partition = warp id % 4: the oscillator shares its sub-partition only with the two
+       light roles (TIME, DEC).  CTAs that share an SM with another CTA (bid >= #SMs) rotate by one warp so the
+       two oscillators sit on different sub-partitions. */
+    const int rw = (warp + 12 - (blockIdx.x >= 148 ? 1 : 0)) % 12;
     int role, ridx;                                                     /* ridx: index inside the role's group */
-    switch (rw) {
+    switch (rw) {      /* sub-partition 0: OSC, DEC (light), one idle warp | 1: TIME, CONS, CONS | 2: CONS, EST, EST | 3: CONS, EST, EST */
         case 0: role = ROLE_OSC; ridx = 0; break;
         case 4: role = ROLE_DEC; ridx = 0; break;
-        case 2: role = ROLE_TIME; ridx = 0; break;
-        case 6: role = ROLE_CONS; ridx = 0; break;
-        case 10: role = ROLE_CONS; ridx = 1; break;
-        case 14: role = ROLE_CONS; ridx = 2; break;
-        case 3: role = ROLE_EST; ridx = 0; break;
-        case 7: role = ROLE_EST; ridx = 1; break;
-        case 11: role = ROLE_EST; ridx = 2; break;
-        case 15: role = ROLE_EST; ridx = 3; break;
-        default: role = ROLE_IDLE; ridx = 0; break;    /* rw 8, 12 (with OSC) and 1, 5, 9, 13 (the other CTA's OSC sub-partition) */
+        case 8: role = ROLE_IDLE; ridx = 0; break;
+        case 1: role = ROLE_TIME; ridx = 0; break;
+        case 5: role = ROLE_CONS; ridx = 0; break;
+        case 9: role = ROLE_CONS; ridx = 1; break;
+        case 2: role = ROLE_CONS; ridx = 2; break;
+        case 3: role = ROLE_CONS; ridx = 3; break;
+        case 6: role = ROLE_EST; ridx = 0; break;
+        case 10: role = ROLE_EST; ridx = 1; break;
+        case 7: role = ROLE_EST; ridx = 2; break;
+        default: role = ROLE_EST; ridx = 3; break;     /* rw == 11 */
     }
     unsigned char *outb = (unsigned char *)p.out + (long long)c * p.out_stride * (p.soft ? 4 : 1);
 
