@@ -235,7 +235,9 @@ extern "C" int b200fsk_create(b200fsk_t **out, const b200fsk_cfg_t *cfg, int nch
     }
     int maxsmem = 0;
     CK(cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-    if (h->smem + 256 > (size_t)maxsmem) { delete h; return fail(B200FSK_ENOMEM, "frame working set %zu B exceeds shared memory %d B", h->smem, maxsmem); }
+    const bool serial_fits = h->smem + 256 <= (size_t)maxsmem;
+    if (h->use_pipe && h->smem_pipe + 1024 > (size_t)maxsmem) h->use_pipe = false;
+    if (!h->use_pipe && !serial_fits) { delete h; return fail(B200FSK_ENOMEM, "frame working set %zu B exceeds shared memory %d B", h->smem, maxsmem); }
     /* the attribute is per function, not per handle: always allow the device maximum so handles of different sizes coexist */
     CK(allow_max_smem((const void *)fsk_demod_kernel, maxsmem));
     if (h->use_pipe) {

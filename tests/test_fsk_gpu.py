@@ -214,3 +214,53 @@ def test_mixed_2fsk_4fsk_batch(cuda):
     for c in range(len(names)):
         assert got[c].tobytes() == ref[c].tobytes(), names[c]
     mb.close()
+
+
+def test_empty_and_sub_frame_pushes(cuda):
+    """Edge cases of the stream interface: zero-length pushes, pushes shorter than a frame (nothing may come out until a
+    whole frame is available), and sample-by-sample feeding around a frame boundary."""
+    cfg = po.RS41
+    iq = siggen.fsk_iq(91, 12_500, ebno_db=12.0)
+    ref, _, recs = po.Oracle(cfg).run_stream(iq)
+    b = make_batch(cfg, 1)
+    out, fr = b.push(iq[None, :0], "cs16")
+    assert fr[0] == 0
+    got = []
+    cuts = [0, 1, 2, 2999, 3000, 3001, 3002, 5990, 6010, 9000, 9001, 12_500]
+    for a, c in zip(cuts[:-1], cuts[1:]):
+        out, fr = b.push(iq[None, a:c], "cs16")
+        got.append(out[0, : fr[0] * b.Nbits].copy())
+        out, fr = b.push(iq[None, :0], "cs16")            # an empty push in between changes nothing
+        assert fr[0] == 0
+    assert np.concatenate(got).tobytes() == ref.tobytes() and len(recs) == 4
+
+
+def test_more_channels_than_resident_ctas(cuda):
+    """600 channels > 2 CTAs x 148 SMs: several waves of channel CTAs, every channel still bit-exact; ragged content
+    (noise-only, different SNR / ppm / offsets) exercises different nin sequences per channel."""
+    cfg = po.RS41
+    nchan, nsamp = 600, 40_000
+    iq = siggen.fsk_batch(5150, nchan, nsamp)
+    iq[7] = siggen.noise_iq(1, nsamp); iq[311] = siggen.noise_iq(2, nsamp); iq[599] = siggen.noise_iq(3, nsamp)
+    b = make_batch(cfg, nchan)
+    out, frames = b.push(iq, "cs16")
+    for c in list(range(0, nchan, 37)) + [7, 311, 599]:
+        ref, _, recs = po.Oracle(cfg).run_stream(iq[c])
+        assert frames[c] == len(recs) and out[c, : frames[c] * b.Nbits].tobytes() == ref.tobytes(), c
+
+
+def test_nin_dependent_window_count_uses_the_serial_kernel(cuda):
+    """Nsym=64 at Ts=10: floor(nin/64) is 9 for nin=635 and 10 for nin=645, so the number of FFT windows depends on nin and
+    the pipelined kernel is not eligible -> the library must fall back to the serial kernel transparently."""
+    cfg = po.FskConfig(48000, 4800, 2, 10, 64, -5000, 5000)
+    iq = siggen.fsk_iq(77, 120_000, ebno_db=12.0)
+    ref, _, recs = po.Oracle(cfg).run_stream(iq)
+    b = make_batch(cfg, 2)
+    out, fr = b.push(np.stack([iq, iq]), "cs16")
+    assert fr[0] == fr[1] == len(recs) > 0
+    assert out[0, : fr[0] * b.Nbits].tobytes() == ref.tobytes() and out[1, : fr[1] * b.Nbits].tobytes() == ref.tobytes()
+
+
+def test_configuration_too_large_for_shared_memory_is_an_error(cuda):
+    with pytest.raises(fsk.B200Error, match="error -3"):
+        fsk.FskBatch(96000, 2400, 4, 10, 600, nchan=1)
