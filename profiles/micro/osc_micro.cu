@@ -40,12 +40,28 @@ template <int MODE> __global__ void k(float2 *out, const float2 *dtab, long long
                     *(unsigned long long *)(dst + j) = p;
                 }
                 ph = make_float2(__uint_as_float((unsigned)p), __uint_as_float((unsigned)(p >> 32)));
+            } else if (MODE == 4) {    // packed products (FMUL2 x2) + scalar adds, STS.128 per 2 steps
+                const unsigned long long drr = pk(d.x, d.x), dii = pk(-d.y, d.y);
+#pragma unroll 4
+                for (int j = 0; j < STEPS; j += 2) {
+                    unsigned long long p = pk(ph.x, ph.y), ps = pk(ph.y, ph.x);
+                    unsigned long long t = mul2(p, drr), u = mul2(ps, dii);
+                    float2 a = make_float2(__fadd_rn(__uint_as_float((unsigned)t), __uint_as_float((unsigned)u)),
+                                           __fadd_rn(__uint_as_float((unsigned)(t >> 32)), __uint_as_float((unsigned)(u >> 32))));
+                    p = pk(a.x, a.y); ps = pk(a.y, a.x);
+                    t = mul2(p, drr); u = mul2(ps, dii);
+                    ph = make_float2(__fadd_rn(__uint_as_float((unsigned)t), __uint_as_float((unsigned)u)),
+                                     __fadd_rn(__uint_as_float((unsigned)(t >> 32)), __uint_as_float((unsigned)(u >> 32))));
+                    *(float4 *)(dst + j) = make_float4(a.x, a.y, ph.x, ph.y);
+                }
             } else if (MODE == 3) {    // scalar without any store (pure chain)
 #pragma unroll 8
                 for (int j = 0; j < STEPS; ++j) { ph = cmul_rn(ph, d); }
             }
-            const float av = __fsqrt_rn(__fadd_rn(__fmul_rn(ph.x, ph.x), __fmul_rn(ph.y, ph.y)));
-            ph = make_float2(__fdiv_rn(ph.x, av), __fdiv_rn(ph.y, av));
+            if (r % 7 != 3) {   // keep some un-normalised reps so that rounding differences between variants would show in the result
+                const float av = __fsqrt_rn(__fadd_rn(__fmul_rn(ph.x, ph.x), __fmul_rn(ph.y, ph.y)));
+                ph = make_float2(__fdiv_rn(ph.x, av), __fdiv_rn(ph.y, av));
+            }
         }
     }
     long long t1 = clock64();
@@ -60,14 +76,14 @@ template <int MODE> void run(const char *name, int warps, float2 *out, float2 *d
     if (e != cudaSuccess) { printf("%s: %s\n", name, cudaGetErrorString(e)); return; }
     long long h[8]; float2 o[16];
     cudaMemcpy(h, cyc, sizeof h, cudaMemcpyDeviceToHost); cudaMemcpy(o, out, sizeof o, cudaMemcpyDeviceToHost);
-    printf("%-44s warps=%d  cycles/step: w0=%.2f w%d=%.2f   phi0=(%.9g,%.9g)\n", name, warps, h[0] / double(STEPS * REPS),
+    printf("%-44s warps=%d  cycles/step: w0=%.2f w%d=%.2f   phi0=(%a,%a)\n", name, warps, h[0] / double(STEPS * REPS),
            warps - 1, h[warps - 1] / double(STEPS * REPS), o[0].x, o[0].y);
 }
 int main()
 {
     float2 *out, *dtab; long long *cyc;
     cudaMalloc(&out, 256); cudaMalloc(&dtab, 32); cudaMalloc(&cyc, 64);
-    float2 hd[3] = {{0.951056516f, -0.309016994f}, {0.951056516f, 0.309016994f}, {1.0f, 1.0f}};
+    float2 hd[3] = {{0.9510565f, -0.3090171f}, {0.9510564f, 0.3090169f}, {1.0f, 1.0f}};
     cudaMemcpy(dtab, hd, sizeof hd, cudaMemcpyHostToDevice);
     for (int w : {1, 2, 4, 5, 8}) {
         run<0>("scalar unroll4 STS.64 (current)", w, out, dtab, cyc);
@@ -76,5 +92,7 @@ int main()
     run<2>("packed f32x2 (mul2,mul2,add2 + swap)", 1, out, dtab, cyc);
     run<2>("packed f32x2 (mul2,mul2,add2 + swap)", 4, out, dtab, cyc);
     run<3>("scalar, no store (pure chain)", 1, out, dtab, cyc);
+    run<4>("FMUL2 products + scalar FADD, STS.128/2", 1, out, dtab, cyc);
+    run<4>("FMUL2 products + scalar FADD, STS.128/2", 5, out, dtab, cyc);
     return 0;
 }
