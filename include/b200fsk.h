@@ -130,6 +130,22 @@ int  b200fsk_get_stats(b200fsk_t *h, int chan, b200fsk_stats_t *st);
 /* fsk->Sf of channel c (Ndft floats; the CLI prints the first Ndft/2 as "samp_fft", fsk_demod.c:397-402). */
 int  b200fsk_get_Sf(b200fsk_t *h, int chan, float *Sf_out);
 
+/* ---- next row of the path: soft-bit header sync + RS41 frame assembly, soft bits stay in HBM -----------
+ * Reference: find_softbinhead / corr_softhdb (demod/mod/demod_mod.c:1692-1761) + the --softin frame loop of rs41mod
+ * (demod/mod/rs41mod.c:2875-2960), i.e. what `rs41mod --softin [-i] -r` does with fsk_demod's stdout before its ECC stage.
+ * d_soft: [nchan] rows of `stride` floats as written by b200fsk_demod_device (soft=1); per-channel bit counts in d_nbits
+ * (device, may be NULL -> nbits for all).  softinv = --softinv, inv = -i.  Frames are returned grouped by channel, in order. */
+typedef struct {
+    int   chan, len, nbytes_read;      /* len: 320 or 518 from the frame-type byte; nbytes_read < 518: stream ended inside the frame */
+    long long first_bit;               /* index of the first payload soft bit                                                   */
+    float score;                       /* header correlation                                                                    */
+    unsigned char bytes[518];          /* de-whitened frame (bytes 0..7: header)                                                */
+    float bytescore[518];              /* soft bit of smallest magnitude per byte (input of the reference's ecc3/4 erasure logic) */
+} b200fsk_rs41_frame_t;
+int  b200fsk_rs41_framesync_device(const float *d_soft, long stride, const int *d_nbits, int nbits, int nchan, int softinv, int inv,
+                                   b200fsk_rs41_frame_t *h_frames, int max_frames, int *nframes, int device, void *stream);
+const char *b200fsk_framesync_last_error(void);
+
 /* kernel launches issued by this handle so far (bench.py's gpu_launches) */
 long b200fsk_launch_count(const b200fsk_t *h);
 /* device time (ms) of the most recent demod kernel measured with CUDA events on its own stream; <0 if none */

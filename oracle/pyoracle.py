@@ -309,3 +309,34 @@ def ref_cli_dft_detect(iq: np.ndarray, sample_rate: int = 48000, bw_khz: float =
             dets.append((m.group(1), float(m.group(2)), pos, float(mh.group(1)) if mh else 0.0))
     rc = r.returncode if r.returncode < 128 else r.returncode - 256
     return rc, dets
+
+
+# ------------------------------------------------------------------------------------------------
+# soft-bit header sync + RS41 frame assembly
+# ------------------------------------------------------------------------------------------------
+class SsoFrame(C.Structure):
+    _fields_ = [("len", C.c_int), ("nbytes_read", C.c_int), ("first_bit", C.c_long), ("score", C.c_float),
+                ("bytes", C.c_ubyte * 518), ("bytescore", C.c_float * 518)]
+
+
+def softsync_oracle(soft: np.ndarray, softinv: bool = False, inv: bool = True):
+    """-> [(len, first_bit, score, bytes[len] as numpy uint8)] like `rs41mod --softin -i -r` would print."""
+    L = lib()
+    L.sso_rs41.restype = C.c_int
+    L.sso_rs41.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    soft = np.ascontiguousarray(soft, dtype=np.float32)
+    cap = soft.size // 4000 + 4
+    fr = (SsoFrame * cap)()
+    n = L.sso_rs41(soft.ctypes.data, soft.size, int(softinv), int(inv), fr, cap)
+    return [(f.len, f.first_bit, f.score, np.frombuffer(bytes(f.bytes), np.uint8)[: f.len].copy(), f.nbytes_read) for f in fr[: min(n, cap)]]
+
+
+def ref_cli_rs41mod_raw(soft_bytes: bytes, inv: bool = True):
+    """Run oracle/_ref/rs41mod -r --softin [-i] -> [(hex string, tag)] per printed frame."""
+    exe = os.path.join(REF_DIR, "rs41mod")
+    r = subprocess.run([exe, "-r", "--softin"] + (["-i"] if inv else []), input=soft_bytes, capture_output=True)
+    out = []
+    for ln in r.stdout.decode().splitlines():
+        parts = ln.split(" ", 1)
+        out.append((parts[0], parts[1] if len(parts) > 1 else ""))
+    return out

@@ -357,3 +357,35 @@ class FskMixedBatch:
     def close(self):
         for b in self.batches.values():
             b.close()
+
+
+# ==================================================================================================
+# Soft-bit header sync + RS41 frame assembly on the device
+# ==================================================================================================
+class _Rs41Frame(C.Structure):
+    _fields_ = [("chan", C.c_int), ("len", C.c_int), ("nbytes_read", C.c_int), ("first_bit", C.c_longlong), ("score", C.c_float),
+                ("bytes", C.c_ubyte * 518), ("bytescore", C.c_float * 518)]
+
+
+def rs41_framesync_device(d_soft, stride: int, nbits, nchan: int, softinv: bool = False, inv: bool = True, device: int = 0,
+                          stream=None):
+    """What `rs41mod --softin [-i] -r` extracts from fsk_demod's soft decisions, run on soft bits that are still in HBM.
+    d_soft: torch CUDA float32 tensor [nchan, stride] (or device address); nbits: int (all channels) or torch int32 tensor.
+    Returns a list of (chan, len, first_bit, score, bytes[len] (numpy uint8), nbytes_read)."""
+    L = lib()
+    L.b200fsk_rs41_framesync_device.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                                C.c_int, C.POINTER(C.c_int), C.c_int, C.c_void_p]
+    L.b200fsk_framesync_last_error.restype = C.c_char_p
+    ptr = d_soft.data_ptr() if hasattr(d_soft, "data_ptr") else int(d_soft)
+    if hasattr(nbits, "data_ptr"):
+        pn, nmax = C.c_void_p(nbits.data_ptr()), int(nbits.max().item())
+    else:
+        pn, nmax = None, int(nbits)
+    cap = nchan * (nmax // 4144 + 2)
+    fr = (_Rs41Frame * cap)()
+    n = C.c_int(0)
+    st = C.c_void_p(stream.cuda_stream) if stream is not None and hasattr(stream, "cuda_stream") else None
+    rc = L.b200fsk_rs41_framesync_device(C.c_void_p(ptr), stride, pn, nmax, nchan, int(softinv), int(inv), fr, cap, C.byref(n), device, st)
+    if rc:
+        raise B200Error(f"rs41 framesync error {rc}: {L.b200fsk_framesync_last_error().decode()}")
+    return [(f.chan, f.len, f.first_bit, f.score, np.frombuffer(bytes(f.bytes), np.uint8)[: f.len].copy(), f.nbytes_read) for f in fr[: n.value]]
