@@ -76,6 +76,24 @@ int  b200dft_run_host(b200dft_t *h, const void *h_iq, int fmt, long in_stride, l
 int  b200dft_run_device(b200dft_t *h, const void *d_iq, int fmt, long in_stride, long nsamp, int opt_cont, double tl,
                         b200dft_result_t *res);
 
+/* ---- wideband mode: `dft_detect --IQ <fq> --bw <kHz> [--dc] - <sr_base> <bits>` --------------------------------
+ * The reference translates ONE candidate frequency per process out of a wide capture (rotation LUT + decimating low-pass,
+ * dft_detect.c:751-761, tables :1021-1111; the same front as demod/mod/iq_dec.c:514-545) and then runs the detector at the
+ * IF rate.  Here one handle takes the capture once and nchan values of fq (the --IQ argument: fraction of sr_base, clipped to
+ * +-0.5 like :1388-1389); each result is what the process started with that fq would have printed and returned. */
+typedef struct { int sr_base, if_sr, decM, dectaps, nchan; } b200dft_wbinfo_t;
+int  b200dft_create_wideband(b200dft_t **out, int sr_base, double bw_khz, int opt_dc, int nchan, int device);
+int  b200dft_wideband_info(const b200dft_t *h, b200dft_wbinfo_t *info);
+int  b200dft_run_wideband_host(b200dft_t *h, const void *h_wide, int fmt, long nwide, const double *fq, int opt_cont, double tl,
+                               b200dft_result_t *res);
+int  b200dft_run_wideband_device(b200dft_t *h, const void *d_wide, int fmt, long nwide, const double *fq, int opt_cont, double tl,
+                                 b200dft_result_t *res);
+/* channeliser alone: d_if_out[c*out_stride + m] (float I,Q pairs, device memory) = IF sample m of channel c; *nout = nwide/decM.
+ * This is the stream `iq_dec --iq <fq> - <sr_base> <bits>` would emit before its output conversion (iq_dec.c:514-545). */
+int  b200dft_channelise_device(b200dft_t *h, const void *d_wide, int fmt, long nwide, const double *fq, void *d_if_out, long out_stride,
+                               long *nout);
+int  b200dft_last_channelise_ms(b200dft_t *h, float *ms);
+
 long  b200dft_launch_count(const b200dft_t *h);
 /* device time (ms) of the front-end kernels and of the correlator kernel in the most recent run */
 int   b200dft_last_kernel_ms(b200dft_t *h, float *front_ms, float *corr_ms);

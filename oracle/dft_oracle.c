@@ -68,6 +68,10 @@ typedef struct {
     unsigned rcount; float rbitgrenze;
     /* input */
     const unsigned char *in; long nsamp, rd;
+    /* --IQ <fq> baseband translate + decimate (dft_detect.c:751-761, 1021-1111) */
+    int wide, sr_base, decM, dectaps, lut_len; unsigned sample_decX, sample_decM; double xlt_fq;
+    float *ws_dec; float complex *ex, *decX, *decMbuf;
+    float complex *if_out; long if_cap, if_n;                      /* optional copy of the decimated IF stream */
 } dfto_t;
 
 static void fft_raw(dfto_t *s, float complex *Z)                       /* dft_detect.c:295-329 */
@@ -126,8 +130,38 @@ static double pulse(double t, double sigma) { return Qf((t - 0.5) / sigma) - Qf(
 
 static int init(dfto_t *s)                                              /* dft_detect.c:995-1285, --iq branch */
 {
-    int sr = s->sr, taps, j, i;
+    int taps, j, i;
     float lpIQ_bw[3] = {6e3f, 12e3f, 22e3f}, lpFM_bw[2] = {4e3f, 10e3f};
+    s->decM = 1;
+    if (s->wide) {                                                      /* :1021-1068 */
+        int IF_sr = 48000, decM = 1, sr_base = s->sr;
+        if (s->set_lpIQ > IF_sr) IF_sr = s->set_lpIQ;
+        int wideIF = IF_sr > 60e3;
+        if (IF_sr > sr_base) IF_sr = sr_base;
+        if (IF_sr < sr_base) { while (sr_base % IF_sr) IF_sr += 1; decM = sr_base / IF_sr; }
+        float f_lp = (IF_sr + 20e3) / (4.0 * sr_base), t_bw = (IF_sr - 20e3);
+        if (wideIF) { f_lp = (IF_sr + 60e3) / (4.0 * sr_base); t_bw = (IF_sr - 60e3); }
+        if (t_bw < 0) t_bw = 10e3;
+        t_bw /= sr_base;
+        taps = 4.0 / t_bw; if (taps % 2 == 0) taps++;
+        s->dectaps = lowpass_init(f_lp, taps, &s->ws_dec);
+        s->sr_base = sr_base; s->sr = IF_sr; s->decM = decM;
+        /* rotation look-up table (:1070-1101) */
+        int W = 2 * 8, d, k, freq = (int)(s->xlt_fq * (double)sr_base + 0.5), freq0 = freq;
+        for (d = W; d > 0; d--) if (sr_base % d == 0) break;
+        if (d == 0) d = 1;
+        for (k = 0; k < W / 2; k++) {
+            if ((freq + k) % d == 0) { freq0 = freq + k; break; }
+            if ((freq - k) % d == 0) { freq0 = freq - k; break; }
+        }
+        s->lut_len = sr_base / d;
+        double f0 = freq0 / (double)sr_base;
+        s->ex = (float complex *)calloc(s->lut_len + 1, sizeof(float complex));
+        for (int n = 0; n < s->lut_len; n++) { double t = f0 * (double)n; s->ex[n] = cexp(t * 2 * M_PI * I); }
+        s->decX = (float complex *)calloc(s->dectaps + 1, sizeof(float complex));
+        s->decMbuf = (float complex *)calloc(s->decM + 1, sizeof(float complex));
+    }
+    int sr = s->sr;
     taps = 4 * sr / 2e3; if (taps % 2 == 0) taps++;
     taps = lowpass_init(lpFM_bw[0] / (float)sr, taps, &s->ws_lpFM[0]);
     taps = lowpass_init(lpFM_bw[1] / (float)sr, taps, &s->ws_lpFM[1]);
@@ -138,6 +172,7 @@ static int init(dfto_t *s)                                              /* dft_d
     s->lpIQtaps = taps;
     s->lpIQ_buf = (float complex *)calloc(taps + 3, sizeof(float complex));
     s->maxcnt = sr / 32;
+    if (s->decM > 1) s->maxcnt *= s->decM;                              /* :1156 */
     int hLen = 0, Lmax = 0;
     for (j = 0; j < NRS; j++) {
         s->type[j] = HDR[j].type; s->tn[j] = HDR[j].tn;
@@ -205,10 +240,28 @@ static int read_csample(dfto_t *s, float complex *z)                    /* :556-
     return 0;
 }
 
+static int read_cblock(dfto_t *s)                                      /* f32read_cblock, :593-657 */
+{
+    int n;
+    for (n = 0; n < s->decM; n++) { if (read_csample(s, &s->decMbuf[n])) break; }
+    return n;
+}
+
 static int buf_sample(dfto_t *s)                                        /* f32buf_sample, :737-819 (--iq) */
 {
     float complex z, z_fm0, z_fm1, z_fm2, w; float sv[N_BWIQ]; double gain = FM_GAIN;
-    if (read_csample(s, &z)) return -1;
+    if (s->wide) {                                                      /* :751-761 */
+        if (read_cblock(s) < s->decM) return -1;
+        for (int j = 0; j < s->decM; j++) {
+            s->decX[s->sample_decX] = s->decMbuf[j] * s->ex[s->sample_decM];
+            s->sample_decM += 1; if (s->sample_decM >= (unsigned)s->lut_len) s->sample_decM = 0;
+            s->sample_decX += 1; if (s->sample_decX >= (unsigned)s->dectaps) s->sample_decX = 0;
+        }
+        z = lowpass(s->decX, s->sample_decX, s->dectaps, s->ws_dec);
+        if (s->if_out && s->if_n < s->if_cap) s->if_out[s->if_n] = z;
+        s->if_n++;
+    }
+    else if (read_csample(s, &z)) return -1;
     s->lpIQ_buf[s->sample_in % s->lpIQtaps] = z;
     z_fm0 = lowpass(s->lpIQ_buf, s->sample_in + 1, s->lpIQtaps, s->ws_lpIQ[0]);
     if (s->singleLp) { z_fm1 = z_fm0; z_fm2 = z_fm0; }
@@ -260,7 +313,7 @@ static int get_corr(dfto_t *s, int j, float *maxv, unsigned *maxvpos)    /* getC
     mx /= xnorm * N;
     mpos -= s->lpFMtaps / 2;
     *maxv = mx; *maxvpos = mpos;
-    if (s->opt_dc) s->df[j] = s->dc[j] / (2.0 * FM_GAIN * 1);
+    if (s->opt_dc) s->df[j] = s->dc[j] / (2.0 * FM_GAIN * s->decM);     /* :439 */
     return mp;
 }
 
@@ -306,11 +359,36 @@ static int hw(unsigned b) { int d = 0; for (int i = 0; i < 8; i++) { d += b & 1;
 
 /* Whole run of the detector over an in-memory IQ stream.  Returns the process exit code the reference would
  * return (header_found * tn, :1660-1666); detections (the lines the reference prints) go to dets[]. */
+static int run_core(dfto_t *s, const void *iq, long nsamp, int bits, int sample_rate, double bw_khz, int opt_dc, int opt_cont, double tl,
+                    dfto_det_t *dets, int maxdets, int *ndets, dfto_blk_t *blks, int maxblks, int *nblks);
+
 int dfto_run(const void *iq, long nsamp, int bits, int sample_rate, double bw_khz, int opt_dc, int opt_cont, double tl,
              dfto_det_t *dets, int maxdets, int *ndets, dfto_blk_t *blks, int maxblks, int *nblks)
 {
     dfto_t S; memset(&S, 0, sizeof S);
-    dfto_t *s = &S;
+    return run_core(&S, iq, nsamp, bits, sample_rate, bw_khz, opt_dc, opt_cont, tl, dets, maxdets, ndets, blks, maxblks, nblks);
+}
+
+/* `dft_detect [-c] [-t tl] --IQ fq --bw bw_khz [--dc] - sr_base bits`: translate by -fq*sr_base, decimate to the IF rate,
+ * then the same detector (dft_detect.c:1383-1392).  if_out (may be NULL) receives the decimated IF samples (re,im pairs). */
+int dfto_run_wideband(const void *iq, long nsamp, int bits, int sr_base, double fq, double bw_khz, int opt_dc, int opt_cont, double tl,
+                      dfto_det_t *dets, int maxdets, int *ndets, float *if_out, long if_cap, long *if_n, int *if_sr, int *decM, int *dectaps)
+{
+    dfto_t S; memset(&S, 0, sizeof S);
+    if (fq < -0.5) fq = -0.5;
+    if (fq > 0.5) fq = 0.5;
+    S.wide = 1; S.xlt_fq = -fq; S.if_out = (float complex *)if_out; S.if_cap = if_cap;
+    int rc = run_core(&S, iq, nsamp, bits, sr_base, bw_khz, opt_dc, opt_cont, tl, dets, maxdets, ndets, NULL, 0, NULL);
+    if (if_n) *if_n = S.if_n;
+    if (if_sr) *if_sr = S.sr;
+    if (decM) *decM = S.decM;
+    if (dectaps) *dectaps = S.dectaps;
+    return rc;
+}
+
+static int run_core(dfto_t *s, const void *iq, long nsamp, int bits, int sample_rate, double bw_khz, int opt_dc, int opt_cont, double tl,
+                    dfto_det_t *dets, int maxdets, int *ndets, dfto_blk_t *blks, int maxblks, int *nblks)
+{
     s->sr = sample_rate; s->bits = bits; s->opt_dc = opt_dc; s->opt_cont = opt_cont;
     if (bw_khz < 1.0) bw_khz = 0.0;
     s->set_lpIQ = bw_khz * 1e3; s->in = (const unsigned char *)iq; s->nsamp = nsamp;
@@ -375,7 +453,7 @@ int dfto_run(const void *iq, long nsamp, int bits, int sample_rate, double bw_kh
                 if (mv[jj] > HDR[jj].thres || mv[jj] < -HDR[jj].thres) {
                     if (dets && nd < maxdets) {
                         dfto_det_t *d = &dets[nd];
-                        d->hdr = jj; d->tn = s->tn[jj]; d->score = mv[jj]; d->pos = mv_pos[jj]; d->df_hz = s->df[jj] * s->sr; d->m10 = frm2 & 0xFFFF;
+                        d->hdr = jj; d->tn = s->tn[jj]; d->score = mv[jj]; d->pos = mv_pos[jj]; d->df_hz = s->df[jj] * (s->wide ? s->sr_base : s->sr) /* df*sr_base, :1628 */; d->m10 = frm2 & 0xFFFF;
                         strncpy(d->type, s->type[jj], sizeof d->type - 1); d->type[sizeof d->type - 1] = 0;
                     }
                     nd++;
@@ -399,6 +477,7 @@ ende:
     for (j = 0; j < 3; j++) free(s->ws_lpIQ[j]);
     for (j = 0; j < IDX_RS; j++) free(s->Fm[j]);
     for (j = 0; j < N_BWIQ; j++) free(s->buf_fm[j]);
+    free(s->ws_dec); free(s->ex); free(s->decX); free(s->decMbuf);
     free(s->lpIQ_buf); free(s->rawbits); free(s->xn); free(s->db); free(s->ew); free(s->X); free(s->Z); free(s->cx);
     return rc;
 }

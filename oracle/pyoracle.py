@@ -288,13 +288,36 @@ def dft_oracle_run(iq: np.ndarray, sample_rate: int = 48000, bw_khz: float = 15.
     return rc, out, bl
 
 
+def dft_oracle_run_wideband(iq: np.ndarray, sr_base: int, fq: float, bw_khz: float = 15.0, dc: bool = True, cont: bool = True,
+                            tl: float = -1.0, want_if: bool = False):
+    """`dft_detect --IQ fq ...` restatement -> (exit_code, dets, info dict, IF stream complex64 or None)"""
+    L = lib()
+    L.dfto_run_wideband.restype = C.c_int
+    L.dfto_run_wideband.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double,
+                                    C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_long, C.POINTER(C.c_long),
+                                    C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    iq = np.ascontiguousarray(iq)
+    bits = {np.dtype(np.int16): 16, np.dtype(np.float32): 32, np.dtype(np.uint8): 8}[iq.dtype]
+    nsamp = iq.size // 2
+    dets = (DftDet * 4096)()
+    nd, ifsr, decm, taps, ifn = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0), C.c_long(0)
+    ifbuf = np.zeros(nsamp + 8, dtype=np.complex64) if want_if else None
+    rc = L.dfto_run_wideband(iq.ctypes.data, nsamp, bits, sr_base, fq, bw_khz, int(dc), int(cont), tl, dets, 4096, C.byref(nd),
+                             ifbuf.ctypes.data if want_if else None, nsamp + 8 if want_if else 0, C.byref(ifn),
+                             C.byref(ifsr), C.byref(decm), C.byref(taps))
+    out = [(dets[i].type.decode(), dets[i].score, dets[i].pos, dets[i].df_hz) for i in range(min(nd.value, 4096))]
+    info = {"if_sr": ifsr.value, "decM": decm.value, "dectaps": taps.value, "if_n": ifn.value}
+    return rc, out, info, (ifbuf[: ifn.value] if want_if else None)
+
+
 def ref_cli_dft_detect(iq: np.ndarray, sample_rate: int = 48000, bw_khz: float = 15.0, dc: bool = True, cont: bool = True,
-                       tl: float | None = None, bits: int = 16):
-    """Run oracle/_ref/dft_detect -v on stdin bytes -> (exit_code as signed int8-ish, [(type, score, pos, df_hz)])."""
+                       tl: float | None = None, bits: int = 16, fq: float | None = None):
+    """Run oracle/_ref/dft_detect -v on stdin bytes -> (exit_code as signed int8-ish, [(type, score, pos, df_hz)]).
+    fq given: the baseband translate+decimate mode `--IQ fq` at sample_rate = sr_base."""
     exe = os.path.join(REF_DIR, "dft_detect")
     if not os.path.exists(exe):
         build()
-    args = [exe, "-v"] + (["-c"] if cont else []) + (["-t", str(tl)] if tl is not None else []) + ["--iq", "--bw", str(bw_khz)]
+    args = [exe, "-v"] + (["-c"] if cont else []) + (["-t", str(tl)] if tl is not None else []) + (["--iq"] if fq is None else ["--IQ", repr(float(fq))]) + ["--bw", str(bw_khz)]
     args += (["--dc"] if dc else []) + ["-", str(sample_rate), str(bits)]
     r = subprocess.run(args, input=np.ascontiguousarray(iq).tobytes(), capture_output=True)
     import re

@@ -3,8 +3,9 @@
  * Same stdout lines ("<TYPE>: <score>[ , <+f>Hz]", "sample: N" with -v), same exit code (+-type number).
  * All DSP runs on the GPU through include/b200dft.h.  The stream is analysed incrementally (about half a second
  * at a time) so that, like the reference, the process answers as soon as a header is found when -c is not given.
- * Not supported here (the auto_rx IQ scan never uses them): WAV / FM-audio input, --IQ baseband decimation,
- * running without --bw, -d2, --ch2. */
+ *     dft_detect ... --IQ <fq> --bw <kHz> [--dc] - <sr_base> <bits>   baseband capture: translate by -fq*sr_base, decimate to the IF
+ *                                                                     rate (dft_detect.c:1383-1392), then the same detector
+ * Not supported here (the auto_rx IQ scan never uses them): WAV / FM-audio input, running without --bw, --min, -d2, --ch2. */
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -14,8 +15,8 @@
 
 int main(int argc, char **argv)
 {
-    int verbose = 0, cont = 0, silent = 0, iq = 0, dc = 0, sr = 0, bits = 0, pcmraw = 0;
-    double tl = -1.0, bw = 0.0;
+    int verbose = 0, cont = 0, silent = 0, iq = 0, dc = 0, sr = 0, bits = 0, pcmraw = 0, wide = 0;
+    double tl = -1.0, bw = 0.0, fq = 0.0;
     for (char **a = argv + 1; *a; ++a) {
         if (!strcmp(*a, "-h") || !strcmp(*a, "--help")) {
             fprintf(stderr, "%s [options] - <sr> <bits>   (raw IQ on stdin)\n  options:\n       -v          (verbose)\n       -c          (continuous)\n"
@@ -33,14 +34,20 @@ int main(int argc, char **argv)
             if (!*++a) return -1; bits = atoi(*a);
             if (sr < 1 || (bits != 8 && bits != 16 && bits != 32)) { fprintf(stderr, "- <sr> <bs>\n"); return -1; }
             pcmraw = 1;
-        } else if (!strcmp(*a, "--IQ") || !strcmp(*a, "--ths") ) { fprintf(stderr, "dft_detect(b200): option %s not supported\n", *a); return -50; }
+        } else if (!strcmp(*a, "--IQ")) { if (!*++a) return -1; fq = atof(*a); iq = 1; wide = 1; }
+        else if (!strcmp(*a, "--ths")) { fprintf(stderr, "dft_detect(b200): option %s not supported\n", *a); return -50; }
         else if (!strcmp(*a, "--min") || !strcmp(*a, "-L") || !strcmp(*a, "-d2") || !strcmp(*a, "--ch2")) { fprintf(stderr, "dft_detect(b200): option %s not supported\n", *a); return -50; }
         else { fprintf(stderr, "dft_detect(b200): file/WAV input not supported, use: --iq --bw <kHz> - <sr> <bits>\n"); return -50; }
     }
     setbuf(stdout, NULL);
     if (!pcmraw || !iq || bw <= 0.0) { fprintf(stderr, "dft_detect(b200): needs --iq --bw <kHz> - <sr> <bits>\n"); return -50; }
     b200dft_t *h = NULL;
-    if (b200dft_create(&h, sr, bw, dc, 1, 0) != B200DFT_OK) { fprintf(stderr, "error: init buffers (%s)\n", b200dft_last_error()); return -50; }
+    const int crc = wide ? b200dft_create_wideband(&h, sr, bw, dc, 1, 0) : b200dft_create(&h, sr, bw, dc, 1, 0);
+    if (crc != B200DFT_OK) { fprintf(stderr, "error: init buffers (%s)\n", b200dft_last_error()); return -50; }
+    if (wide) {                                         /* -t counts IF samples (:1494) = (tl+1)*sr input samples, sr = IF*dec */
+        b200dft_wbinfo_t wb; b200dft_wideband_info(h, &wb);
+        fprintf(stderr, "IF: %d\n", wb.if_sr); fprintf(stderr, "dec: %d\n", wb.decM);      /* :1067-1068 */
+    }
     const int fmt = bits == 16 ? B200DFT_FMT_CS16 : (bits == 32 ? B200DFT_FMT_F32 : B200DFT_FMT_CU8), es = bits / 4;
     long cap = (tl > 0 ? (long)((tl + 1) * sr) + 16 : (long)60 * sr), n = 0, step = sr / 2, next = step;
     unsigned char *buf = malloc((size_t)cap * es);
@@ -56,7 +63,8 @@ int main(int argc, char **argv)
             n += bytes / es;
         }
         if (n >= cap && tl <= 0) { cap *= 2; buf = realloc(buf, (size_t)cap * es); }
-        if (b200dft_run_host(h, buf, fmt, n, n, cont, tl, &res) != B200DFT_OK) { fprintf(stderr, "dft_detect(b200): %s\n", b200dft_last_error()); return -50; }
+        const int rrc = wide ? b200dft_run_wideband_host(h, buf, fmt, n, &fq, cont, tl, &res) : b200dft_run_host(h, buf, fmt, n, n, cont, tl, &res);
+        if (rrc != B200DFT_OK) { fprintf(stderr, "dft_detect(b200): %s\n", b200dft_last_error()); return -50; }
         for (int i = printed; i < res.ndet && i < B200DFT_MAXDET; i++) {            /* dft_detect.c:1620-1634 */
             const b200dft_det_t *d = &res.dets[i];
             if (silent) continue;

@@ -129,6 +129,69 @@ __global__ void dft_dcavg_kernel(const DftParams p)
     }
 }
 
+
+/* ---- KW: wideband front (dft_detect --IQ <fq>): DC block on the shared capture, rotate by the per-channel LUT phase, decimating FIR
+ *          (dft_detect.c:751-761 with the tables of :1021-1111).  One CTA = one channel x CH_TM outputs; the rotated window is
+ *          staged once in shared memory, each warp then forms whole outputs (lanes stride the taps, conflict-free float2 reads). */
+#define CH_THREADS 256
+struct ChanParams {
+    const void *wide; int fmt; long long nwide;
+    const float2 *wavg; int wmaxcnt;          /* IQdc means of the wide stream (maxcnt = IF_sr/32*decM, :1155-1156) */
+    int decM, taps, lut_len, TM;
+    const float *ws;                          /* decimation low-pass (:1043-1058) */
+    const double *f0;                         /* [nchan] freq0/sr_base of the rotation LUT (:1075-1096) */
+    float2 *out; long long nout, out_stride;
+};
+
+/* (cos,sin)(t*2*pi) for the LUT entry ex[n], t = f0*n, formed like the reference's cexp(t*2*M_PI*I) (:1100): the double argument is
+ * reduced with a three-term 2*pi (FMA keeps each product exact), then the fast-path sincos. */
+__device__ __forceinline__ float2 lut_entry(double f0, int n)
+{
+    const double t = f0 * (double)n;
+    const double arg = (t * 2) * M_PI;
+    const double k = rint(arg * 0.15915494309189535);
+    double r = fma(-k, 6.283185307179586232e+00, arg);
+    r = fma(-k, 2.449293598294706414e-16, r);
+    r = fma(-k, -5.989539619436679332e-33, r);
+    double sn, cs;
+    sincos(r, &sn, &cs);
+    return make_float2((float)cs, (float)sn);
+}
+
+__global__ void __launch_bounds__(CH_THREADS) dft_chan_kernel(const ChanParams q)
+{
+    extern __shared__ float2 xs[];
+    const int c = blockIdx.y, decM = q.decM, taps = q.taps;
+    const long long m0 = (long long)blockIdx.x * q.TM;
+    const int tm = (int)min((long long)q.TM, q.nout - m0);
+    const int W = (tm - 1) * decM + taps;
+    float *wsm = (float *)(xs + (q.TM - 1) * decM + taps);
+    const long long g0 = m0 * decM + decM - taps;                /* wide index of xs[0]; output m ends at wide sample m*decM+decM-1 */
+    const double f0 = q.f0[c];
+    for (int i = threadIdx.x; i < taps; i += CH_THREADS) wsm[i] = q.ws[i];
+    for (int i = threadIdx.x; i < W; i += CH_THREADS) {
+        const long long g = g0 + i;
+        float2 v = make_float2(0.f, 0.f);
+        if (g >= 0) {
+            const float2 r = dft_load(q.wide, q.fmt, g);
+            const float2 a = q.wavg[g / q.wmaxcnt];
+            const float x = r.x - a.x, y = r.y - a.y;                                  /* :627-628 */
+            const float2 e = lut_entry(f0, (int)(g % q.lut_len));
+            v = make_float2(x * e.x - y * e.y, x * e.y + y * e.x);                     /* decMbuf[j]*ex[] (:755) */
+        }
+        xs[i] = v;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = warp; o < tm; o += CH_THREADS / 32) {
+        const float2 *xp = xs + o * decM;
+        float ax = 0.f, ay = 0.f;
+        for (int i = lane; i < taps; i += 32) { const float w = wsm[i]; const float2 v = xp[i]; ax = fmaf(w, v.x, ax); ay = fmaf(w, v.y, ay); }
+        for (int d = 16; d; d >>= 1) { ax += __shfl_xor_sync(0xffffffffu, ax, d); ay += __shfl_xor_sync(0xffffffffu, ay, d); }
+        if (lane == 0) q.out[(long long)c * q.out_stride + m0 + o] = make_float2(ax, ay);
+    }
+}
+
 /* ---- K1: fused front end: DC subtraction -> IF FIR -> FM discriminator (filtered + unfiltered) ------------------ */
 __global__ void __launch_bounds__(FRONT_TILE) dft_front_kernel(const DftParams p)
 {
@@ -376,6 +439,11 @@ struct b200dft {
     size_t corr_smem_max = 0;
     cudaStream_t stream = 0; cudaEvent_t ev[4] = {0, 0, 0, 0};
     long launches = 0; bool timed = false;
+    /* wideband (--IQ) mode */
+    bool wide = false; int sr_base = 0, decM = 1, dectaps = 0, wmaxcnt = 0, ch_tm = 0; size_t ch_smem = 0;
+    float *d_ws_dec = 0; double *d_f0 = 0; float2 *d_wavg = 0; float2 *d_if = 0; void *d_wide = 0;
+    long long cap_wavg = 0, cap_if = 0, cap_wide_bytes = 0;
+    cudaEvent_t evc[2] = {0, 0}; bool ch_timed = false;
 };
 
 static double sinc_(double x) { return x == 0 ? 1 : sin(M_PI * x) / (M_PI * x); }
@@ -484,9 +552,11 @@ extern "C" void b200dft_destroy(b200dft_t *h)
 {
     if (!h) return;
     cudaSetDevice(h->device); cudaDeviceSynchronize();
-    void *ptrs[] = {h->d_ws_lpIQ, h->d_ws_lpFM, h->d_match, h->d_hdr, h->d_avg, h->d_fm_filt, h->d_fm_raw, h->d_res, h->d_iq, h->d_list, h->d_soff};
+    void *ptrs[] = {h->d_ws_lpIQ, h->d_ws_lpFM, h->d_match, h->d_hdr, h->d_avg, h->d_fm_filt, h->d_fm_raw, h->d_res, h->d_iq, h->d_list, h->d_soff,
+                    h->d_ws_dec, h->d_f0, h->d_wavg, h->d_if, h->d_wide};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < 4; i++) cudaEventDestroy(h->ev[i]);
+    for (int i = 0; i < 2; i++) if (h->evc[i]) cudaEventDestroy(h->evc[i]);
     cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -528,7 +598,7 @@ static void chan_report(const b200dft *h, ChanRun &s, int j)                 /* 
     if (s.mv[j] > HDR[j].thres || s.mv[j] < -HDR[j].thres) {
         if (s.out->ndet < B200DFT_MAXDET) {
             b200dft_det_t *d = &s.out->dets[s.out->ndet];
-            d->hdr = j; d->tn = s.tn[j]; d->score = s.mv[j]; d->pos = s.mv_pos[j]; d->df_hz = s.dfv[j] * h->sr; d->m10 = s.frm2 & 0xFFFF;
+            d->hdr = j; d->tn = s.tn[j]; d->score = s.mv[j]; d->pos = s.mv_pos[j]; d->df_hz = s.dfv[j] * (h->wide ? h->sr_base : h->sr); d->m10 = s.frm2 & 0xFFFF;
             memset(d->type, 0, sizeof d->type); strncpy(d->type, s.type[j], sizeof d->type - 1);
         }
         s.out->ndet++;
@@ -579,7 +649,7 @@ static void chan_advance(b200dft *h, ChanRun &s, const BlkRes *res, int nblk_lau
             s.mv0_pos[j] = s.mv_pos[j];
             s.mp[j] = rb[a].mp; s.dcv[j] = rb[a].dc;
             if (rb[a].mp > 0) { s.mv[j] = rb[a].score; s.mv_pos[j] = rb[a].pos; }   /* getCorrDFT leaves them untouched on failure */
-            if (h->opt_dc) s.dfv[j] = s.dcv[j] / (2.0 * FM_GAIN * 1);
+            if (h->opt_dc) s.dfv[j] = s.dcv[j] / (2.0 * FM_GAIN * h->decM);            /* :439 */
         }
         s.b++;
         int header_found = 0;
@@ -606,7 +676,8 @@ static void chan_advance(b200dft *h, ChanRun &s, const BlkRes *res, int nblk_lau
     }
 }
 
-static int run_common(b200dft *h, const void *d_iq, int fmt, long in_stride, long nsamp, int opt_cont, double tl, b200dft_result_t *res)
+static int run_common(b200dft *h, const void *d_iq, int fmt, long in_stride, long nsamp, int opt_cont, double tl, b200dft_result_t *res,
+                      bool skip_iqdc = false)
 {
     /* -t: blocks only trigger while sample_in <= (tl+1)*sr (:1494) */
     long neff = nsamp;
@@ -633,7 +704,8 @@ static int run_common(b200dft *h, const void *d_iq, int fmt, long in_stride, lon
     CK(cudaEventRecord(h->ev[0], s));
     if (neff > 0) {
         dim3 g0((unsigned)(navg - 1), h->nchan);
-        dft_dcavg_kernel<<<g0, 128, 0, s>>>(p);
+        if (skip_iqdc) CK(cudaMemsetAsync(h->d_avg, 0, (size_t)h->nchan * navg * sizeof(float2), s));   /* --IQ: the DC block ran on the wide stream */
+        else dft_dcavg_kernel<<<g0, 128, 0, s>>>(p);
         dim3 g1((unsigned)((neff + FRONT_TILE - 1) / FRONT_TILE), h->nchan);
         const size_t sm1 = (size_t)(2 * FRONT_TILE + h->lpIQtaps + 1) * sizeof(float2);
         dft_front_kernel<<<g1, FRONT_TILE, sm1, s>>>(p);
@@ -732,6 +804,143 @@ extern "C" int b200dft_run_host(b200dft_t *h, const void *h_iq, int fmt, long in
     if (nsamp > 0)
         CK(cudaMemcpy2DAsync(h->d_iq, (size_t)nsamp * es, h_iq, (size_t)in_stride * es, (size_t)nsamp * es, h->nchan, cudaMemcpyHostToDevice, h->stream));
     return run_common(h, h->d_iq, fmt, nsamp, nsamp, opt_cont, tl, res);
+}
+
+
+/* ---- wideband mode: `dft_detect --IQ <fq> --bw <kHz> [--dc] - <sr_base> <bits>` for nchan values of fq over ONE capture ------------- */
+extern "C" int b200dft_create_wideband(b200dft_t **out, int sr_base, double bw_khz, int opt_dc, int nchan, int device)
+{
+    if (!out || sr_base < 1 || nchan <= 0) return fail(B200DFT_EINVAL, "bad arguments");
+    /* IF rate, decimation and low-pass exactly as init_buffers() derives them (dft_detect.c:1021-1068) */
+    int IF_sr = 48000, decM = 1;
+    const float set_lpIQ = bw_khz * 1e3;
+    if (set_lpIQ > IF_sr) IF_sr = set_lpIQ;
+    const int wideIF = IF_sr > 60e3;
+    if (IF_sr > sr_base) IF_sr = sr_base;
+    if (IF_sr < sr_base) { while (sr_base % IF_sr) IF_sr += 1; decM = sr_base / IF_sr; }
+    float f_lp = (IF_sr + 20e3) / (4.0 * sr_base), t_bw = (IF_sr - 20e3);
+    if (wideIF) { f_lp = (IF_sr + 60e3) / (4.0 * sr_base); t_bw = (IF_sr - 60e3); }
+    if (t_bw < 0) t_bw = 10e3;
+    t_bw /= sr_base;
+    int taps = 4.0 / t_bw; if (taps % 2 == 0) taps++;
+    std::vector<float> ws;
+    taps = lowpass_init(f_lp, taps, ws);
+    const int rc = b200dft_create(out, IF_sr, bw_khz, opt_dc, nchan, device);
+    if (rc) return rc;
+    b200dft *h = *out;
+    h->wide = true; h->sr_base = sr_base; h->decM = decM; h->dectaps = taps;
+    h->wmaxcnt = IF_sr / 32; if (decM > 1) h->wmaxcnt *= decM;                     /* :1155-1156 */
+    int maxsmem = 0;
+    CK(cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    int tm = 64;                                                                   /* outputs per CTA: window <= ~96 KB */
+    while (tm > 1 && ((size_t)(tm - 1) * decM + taps) * sizeof(float2) > 96 * 1024) tm >>= 1;
+    h->ch_tm = tm; h->ch_smem = ((size_t)(tm - 1) * decM + taps) * sizeof(float2) + (size_t)taps * sizeof(float) + 16;
+    if (h->ch_smem + 1024 > (size_t)maxsmem) { b200dft_destroy(h); *out = 0; return fail(B200DFT_EINVAL, "decimation filter does not fit shared memory"); }
+    CK(cudaFuncSetAttribute(dft_chan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsmem));
+    CK(cudaMalloc(&h->d_ws_dec, ws.size() * 4)); CK(cudaMemcpy(h->d_ws_dec, ws.data(), (size_t)taps * 4, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&h->d_f0, sizeof(double) * nchan));
+    for (int i = 0; i < 2; i++) CK(cudaEventCreate(&h->evc[i]));
+    return B200DFT_OK;
+}
+
+extern "C" int b200dft_wideband_info(const b200dft_t *h, b200dft_wbinfo_t *info)
+{
+    if (!h || !info || !h->wide) return fail(B200DFT_EINVAL, "not a wideband handle");
+    info->sr_base = h->sr_base; info->if_sr = h->sr; info->decM = h->decM; info->dectaps = h->dectaps; info->nchan = h->nchan;
+    return B200DFT_OK;
+}
+
+/* rotation frequency of the LUT: freq0/sr_base with freq0 snapped like :1072-1096 */
+static double wb_f0(int sr_base, double fq, int *lut_len)
+{
+    if (fq < -0.5) fq = -0.5;
+    if (fq > 0.5) fq = 0.5;
+    const double xlt = -fq;                                                        /* :1390 */
+    const int W = 2 * 8;
+    int d, k, freq = (int)(xlt * (double)sr_base + 0.5), freq0 = freq;
+    for (d = W; d > 0; d--) if (sr_base % d == 0) break;
+    if (d == 0) d = 1;
+    for (k = 0; k < W / 2; k++) {
+        if ((freq + k) % d == 0) { freq0 = freq + k; break; }
+        if ((freq - k) % d == 0) { freq0 = freq - k; break; }
+    }
+    *lut_len = sr_base / d;
+    return freq0 / (double)sr_base;
+}
+
+static int channelise_common(b200dft *h, const void *d_wide, int fmt, long nwide, const double *fq, float2 *d_out, long out_stride, long nout)
+{
+    std::vector<double> f0(h->nchan); int lut_len = 1;
+    for (int c = 0; c < h->nchan; c++) f0[c] = wb_f0(h->sr_base, fq[c], &lut_len);
+    cudaStream_t s = h->stream;
+    CK(cudaMemcpyAsync(h->d_f0, f0.data(), sizeof(double) * h->nchan, cudaMemcpyHostToDevice, s));
+    const long long nwavg = nwide / h->wmaxcnt + 2;
+    if (nwavg > h->cap_wavg) { if (h->d_wavg) cudaFree(h->d_wavg); CK(cudaMalloc(&h->d_wavg, nwavg * sizeof(float2))); h->cap_wavg = nwavg; }
+    CK(cudaEventRecord(h->evc[0], s));
+    if (nout > 0) {
+        DftParams p; memset(&p, 0, sizeof p);
+        p.nchan = 1; p.maxcnt = h->wmaxcnt; p.nsamp = nwide; p.in_stride = 0; p.fmt = fmt; p.iq = d_wide; p.avg = h->d_wavg; p.navg = (int)nwavg;
+        dft_dcavg_kernel<<<dim3((unsigned)(nwavg - 1), 1), 128, 0, s>>>(p);
+        ChanParams q; memset(&q, 0, sizeof q);
+        q.wide = d_wide; q.fmt = fmt; q.nwide = nwide; q.wavg = h->d_wavg; q.wmaxcnt = h->wmaxcnt; q.decM = h->decM; q.taps = h->dectaps;
+        q.lut_len = lut_len; q.TM = h->ch_tm; q.ws = h->d_ws_dec; q.f0 = h->d_f0; q.out = d_out; q.nout = nout; q.out_stride = out_stride;
+        dft_chan_kernel<<<dim3((unsigned)((nout + h->ch_tm - 1) / h->ch_tm), h->nchan), CH_THREADS, h->ch_smem, s>>>(q);
+        h->launches += 2;
+    }
+    CK(cudaEventRecord(h->evc[1], s));
+    CK(cudaGetLastError());
+    h->ch_timed = true;
+    return B200DFT_OK;
+}
+
+extern "C" int b200dft_channelise_device(b200dft_t *h, const void *d_wide, int fmt, long nwide, const double *fq, void *d_if_out, long out_stride,
+                                         long *nout)
+{
+    if (!h || !h->wide || !d_wide || !fq || !d_if_out) return fail(B200DFT_EINVAL, "null / not a wideband handle");
+    if (fmt < 0 || fmt > 2 || nwide < 0) return fail(B200DFT_ERANGE, "fmt/nwide");
+    CK(cudaSetDevice(h->device));
+    const long n = nwide / h->decM;                                                /* f32read_cblock: only whole blocks (:754) */
+    if (out_stride < n) return fail(B200DFT_ERANGE, "out_stride");
+    const int rc = channelise_common(h, d_wide, fmt, nwide, fq, (float2 *)d_if_out, out_stride, n);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    if (nout) *nout = n;
+    return B200DFT_OK;
+}
+
+extern "C" int b200dft_run_wideband_device(b200dft_t *h, const void *d_wide, int fmt, long nwide, const double *fq, int opt_cont, double tl,
+                                           b200dft_result_t *res)
+{
+    if (!h || !h->wide || !d_wide || !fq || !res) return fail(B200DFT_EINVAL, "null / not a wideband handle");
+    if (fmt < 0 || fmt > 2 || nwide < 0) return fail(B200DFT_ERANGE, "fmt/nwide");
+    CK(cudaSetDevice(h->device));
+    long n = nwide / h->decM;
+    if (tl > 0) { const long lim = (long)floor((tl + 1) * h->sr); if (n > lim) n = lim; }     /* nothing later can trigger (:1494) */
+    if (n > h->cap_if) { if (h->d_if) cudaFree(h->d_if); CK(cudaMalloc(&h->d_if, (size_t)h->nchan * (n + 1) * sizeof(float2))); h->cap_if = n; }
+    const int rc = channelise_common(h, d_wide, fmt, nwide, fq, h->d_if, n, n);
+    if (rc) return rc;
+    return run_common(h, h->d_if, B200DFT_FMT_F32, n, n, opt_cont, tl, res, true);
+}
+
+extern "C" int b200dft_run_wideband_host(b200dft_t *h, const void *h_wide, int fmt, long nwide, const double *fq, int opt_cont, double tl,
+                                         b200dft_result_t *res)
+{
+    if (!h || !h->wide || !h_wide || !fq || !res) return fail(B200DFT_EINVAL, "null / not a wideband handle");
+    if (fmt < 0 || fmt > 2 || nwide < 0) return fail(B200DFT_ERANGE, "fmt/nwide");
+    CK(cudaSetDevice(h->device));
+    const int es = fmt == 1 ? 8 : (fmt == 0 ? 4 : 2);
+    const size_t need = (size_t)nwide * es;
+    if ((long long)need > h->cap_wide_bytes) { if (h->d_wide) cudaFree(h->d_wide); CK(cudaMalloc(&h->d_wide, need + 16)); h->cap_wide_bytes = need; }
+    if (nwide > 0) CK(cudaMemcpyAsync(h->d_wide, h_wide, need, cudaMemcpyHostToDevice, h->stream));
+    return b200dft_run_wideband_device(h, h->d_wide, fmt, nwide, fq, opt_cont, tl, res);
+}
+
+extern "C" int b200dft_last_channelise_ms(b200dft_t *h, float *ms)
+{
+    if (!h || !h->ch_timed || !ms) return fail(B200DFT_EINVAL, "no channeliser run yet");
+    CK(cudaEventSynchronize(h->evc[1]));
+    CK(cudaEventElapsedTime(ms, h->evc[0], h->evc[1]));
+    return B200DFT_OK;
 }
 
 extern "C" long b200dft_launch_count(const b200dft_t *h) { return h ? h->launches : 0; }

@@ -42,9 +42,20 @@
 
 #define PIPE_THREADS 384        /* 12 warps: OSC 1, TIME 1, DEC 1, CONS 4, EST 4, 1 idle (keeps the oscillator's sub-partition quiet) */
 #define PIPE_R    1024          /* ring capacity per tone, samples (power of two, multiple of PIPE_BLK) */
-#define PIPE_BLK  128           /* consumer block / oscillator publication granularity                  */
+#define PIPE_BLK  (32 * PIPE_NCONS)   /* consumer block = one sample per CONS thread */
+#ifndef PIPE_VARIANT
+#define PIPE_VARIANT 0
+#endif
+#if PIPE_VARIANT == 1          /* experiment: 5 EST warps, no idle warp */
+#define PIPE_NEST 5
+#define PIPE_NCONS 4
+#elif PIPE_VARIANT == 2        /* experiment: 3 CONS (96-sample blocks), 5 EST, idle kept */
+#define PIPE_NEST 5
+#define PIPE_NCONS 3
+#else
 #define PIPE_NEST 4             /* EST warps  */
 #define PIPE_NCONS 4            /* CONS warps */
+#endif
 #define PIPE_TB   64            /* timing terms per batch */
 #define PIPE_OSC_CHUNK 256       /* oscillator steps between flow-control checks / position publications */
 #define PIPE_NFB  3             /* FFTs a warp advances together */
@@ -187,12 +198,20 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
     switch (rw) {      /* sub-partition 0: OSC, DEC (light), one idle warp | 1: TIME, CONS, CONS | 2: CONS, EST, EST | 3: CONS, EST, EST */
         case 0: role = ROLE_OSC; ridx = 0; break;
         case 4: role = ROLE_DEC; ridx = 0; break;
+#if PIPE_VARIANT == 1
+        case 8: role = ROLE_EST; ridx = 4; break;
+#else
         case 8: role = ROLE_IDLE; ridx = 0; break;
+#endif
         case 1: role = ROLE_TIME; ridx = 0; break;
         case 5: role = ROLE_CONS; ridx = 0; break;
         case 9: role = ROLE_CONS; ridx = 1; break;
         case 2: role = ROLE_CONS; ridx = 2; break;
+#if PIPE_VARIANT == 2
+        case 3: role = ROLE_EST; ridx = 4; break;
+#else
         case 3: role = ROLE_CONS; ridx = 3; break;
+#endif
         case 6: role = ROLE_EST; ridx = 0; break;
         case 10: role = ROLE_EST; ridx = 1; break;
         case 7: role = ROLE_EST; ridx = 2; break;

@@ -36,6 +36,10 @@ class _Info(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("sample_rate", "N_DFT", "K", "L", "M", "delay", "lpIQtaps", "lpFMtaps", "nhdr_active", "nchan")]
 
 
+class _WbInfo(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("sr_base", "if_sr", "decM", "dectaps", "nchan")]
+
+
 @dataclass
 class Detection:
     type: str
@@ -65,6 +69,12 @@ def lib() -> C.CDLL:
         L.b200dft_launch_count.argtypes = [C.c_void_p]
         L.b200dft_launch_count.restype = C.c_long
         L.b200dft_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.b200dft_create_wideband.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_double, C.c_int, C.c_int, C.c_int]
+        L.b200dft_wideband_info.argtypes = [C.c_void_p, C.POINTER(_WbInfo)]
+        L.b200dft_run_wideband_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_long, C.c_void_p, C.c_int, C.c_double, C.c_void_p]
+        L.b200dft_run_wideband_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_long, C.c_void_p, C.c_int, C.c_double, C.c_void_p]
+        L.b200dft_channelise_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_long, C.POINTER(C.c_long)]
+        L.b200dft_last_channelise_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         _lib = L
     return _lib
 
@@ -144,3 +154,58 @@ class DftDetectBatch:
                 ln += f" , {d.df_hz:+.1f}Hz"
             out.append(ln)
         return "\n".join(out) + ("\n" if out else "")
+
+
+class DftWidebandBatch(DftDetectBatch):
+    """``nchan`` x ``dft_detect --IQ <fq> --bw <bw_khz> [--dc] - <sr_base> <bits>`` over ONE wideband capture
+    (dft_detect.c:1383-1392: rotate by -fq*sr_base, decimate to the IF rate, detect).  ``fq`` is the reference's
+    argument: the candidate's offset as a fraction of ``sr_base``."""
+
+    def __init__(self, sr_base: int, bw_khz: float = 15.0, dc: bool = True, nchan: int = 1, device: int = 0):
+        self.L = lib()
+        self.h = C.c_void_p()
+        _ck(self.L.b200dft_create_wideband(C.byref(self.h), sr_base, float(bw_khz), int(dc), nchan, device))
+        info, wb = _Info(), _WbInfo()
+        _ck(self.L.b200dft_info(self.h, C.byref(info)))
+        _ck(self.L.b200dft_wideband_info(self.h, C.byref(wb)))
+        self.info, self.wb = info, wb
+        self.nchan, self.sr_base, self.sample_rate, self.dc = nchan, sr_base, wb.if_sr, dc
+        self.decM, self.dectaps = wb.decM, wb.dectaps
+        self.K, self.N_DFT = info.K, info.N_DFT
+
+    def _fq(self, fq):
+        fq = np.ascontiguousarray(fq, dtype=np.float64)
+        if fq.shape != (self.nchan,):
+            raise B200DftError(f"fq must hold {self.nchan} values")
+        return fq
+
+    def run(self, wide: np.ndarray, fq, cont: bool = False, tl: float = -1.0):
+        """wide: [nwide, 2] int16 / float32 / uint8 host array -> [(exit_code, [Detection...])] per fq."""
+        wide = np.ascontiguousarray(wide)
+        fq = self._fq(fq)
+        res = (_Res * self.nchan)()
+        _ck(self.L.b200dft_run_wideband_host(self.h, wide.ctypes.data, _FMT[wide.dtype], wide.size // 2, fq.ctypes.data, int(cont), float(tl), res))
+        return self._collect(res)
+
+    def run_device(self, d_wide, fmt: str, nwide: int, fq, cont: bool = False, tl: float = -1.0):
+        fq = self._fq(fq)
+        res = (_Res * self.nchan)()
+        ptr = d_wide.data_ptr() if hasattr(d_wide, "data_ptr") else int(d_wide)
+        _ck(self.L.b200dft_run_wideband_device(self.h, C.c_void_p(ptr), {"cs16": 0, "f32": 1, "cu8": 2}[fmt], nwide, fq.ctypes.data,
+                                               int(cont), float(tl), res))
+        return self._collect(res)
+
+    def channelise(self, d_wide, fmt: str, nwide: int, fq, d_out, out_stride: int | None = None) -> int:
+        """IF streams only: d_out (device, float32 [nchan, out_stride, 2]) <- channel c's decimated samples; returns nout."""
+        fq = self._fq(fq)
+        n = C.c_long(0)
+        ptr = d_wide.data_ptr() if hasattr(d_wide, "data_ptr") else int(d_wide)
+        optr = d_out.data_ptr() if hasattr(d_out, "data_ptr") else int(d_out)
+        _ck(self.L.b200dft_channelise_device(self.h, C.c_void_p(ptr), {"cs16": 0, "f32": 1, "cu8": 2}[fmt], nwide, fq.ctypes.data,
+                                             C.c_void_p(optr), out_stride or nwide // self.decM, C.byref(n)))
+        return n.value
+
+    def channelise_ms(self) -> float:
+        ms = C.c_float(0)
+        _ck(self.L.b200dft_last_channelise_ms(self.h, C.byref(ms)))
+        return ms.value

@@ -22,7 +22,7 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200fsk.so")
+LIB_PATH = os.environ.get("B200FSK_LIB", os.path.join(_HERE, "libb200fsk.so"))   # override only for kernel experiments (profiles/)
 
 FMT_CS16, FMT_F32, FMT_CU8, FMT_S16 = 0, 1, 2, 3
 _FMT = {"cs16": 0, "f32": 1, "cu8": 2, "s16": 3}

@@ -152,3 +152,47 @@ def fm_header_iq(seed: int, nsamp: int, kind: str, Fs: int = 48000, dev_hz: floa
     np.rint(out, out=out)
     np.clip(out, -32768, 32767, out=out)
     return out.astype(np.int16)
+
+
+def wideband_mix(seed: int, nsamp: int, sr_base: int, emitters, amp: float = 4000.0, snr_db: float = 20.0,
+                 dev_hz: float = 2400.0, dc: tuple[float, float] = (0.0, 0.0)) -> np.ndarray:
+    """One wideband capture (cs16 [nsamp, 2] at `sr_base`) holding several GFSK sondes: `emitters` is a list of
+    (kind, centre_hz[, tail[, invert]]) with `kind` a HEADER_BANK row.  Each carrier repeats its header like
+    fm_header_iq; noise (per-carrier SNR in the full sr_base bandwidth) and an optional DC offset are added once.
+    Used for the `dft_detect --IQ <fq>` (translate + decimate) path, SURVEY 8f-2."""
+    rng = np.random.default_rng(seed)
+    acc = np.zeros((nsamp, 2), dtype=np.float64)
+    n = np.arange(nsamp, dtype=np.float64)
+    for e in emitters:
+        kind, fc = e[0], float(e[1])
+        tail = e[2] if len(e) > 2 else ""
+        invert = bool(e[3]) if len(e) > 3 else False
+        _, sps, hdr = HEADER_BANK[kind]
+        spb = sr_base / sps
+        nbits = int(nsamp / spb) + 8
+        bits = rng.integers(0, 2, size=nbits, dtype=np.uint8)
+        h = np.frombuffer((hdr + tail).encode(), dtype=np.uint8) - ord("0")
+        period_bits = max(4 * len(h), int(0.25 * sps))
+        for s in range(int(rng.integers(len(h), period_bits)), nbits - len(h), period_bits):
+            bits[s:s + len(h)] = h
+        lvl = bits.astype(np.float64) * 2.0 - 1.0
+        if invert:
+            lvl = -lvl
+        idx = (n / spb + float(rng.uniform(0, 1))).astype(np.int64)
+        f = lvl[idx]
+        w = max(1, int(round(0.6 * spb)))
+        if w > 1:                                        # boxcar via cumulative sum (w can be thousands of samples here)
+            cs = np.concatenate(([0.0], np.cumsum(f)))
+            lo = np.clip(np.arange(nsamp) - w // 2, 0, nsamp)
+            hi = np.clip(np.arange(nsamp) - w // 2 + w, 0, nsamp)
+            f = (cs[hi] - cs[lo]) / w
+        phase = 2.0 * np.pi * (np.cumsum(dev_hz * f) / sr_base + np.remainder(fc * n / sr_base, 1.0)) + float(rng.uniform(0, 2 * np.pi))
+        acc[:, 0] += amp * np.cos(phase)
+        acc[:, 1] += amp * np.sin(phase)
+    sigma = amp / np.sqrt(2.0) / (10.0 ** (snr_db / 20.0))
+    acc += rng.standard_normal((nsamp, 2)) * sigma
+    acc[:, 0] += dc[0]
+    acc[:, 1] += dc[1]
+    np.rint(acc, out=acc)
+    np.clip(acc, -32768, 32767, out=acc)
+    return acc.astype(np.int16)

@@ -4,7 +4,7 @@
 
     python tests/golden/make_golden.py
 
-Outputs (committed): golden_fsk.npz, golden_dft.json.  The inputs are regenerated from seeds by
+Outputs (committed): golden_fsk.npz, golden_dft.json, golden_dft_wb.json.  The inputs are regenerated from seeds by
 radiosonde_auto_rx_b200.siggen, so only outputs + an input checksum are stored.
 """
 import hashlib
@@ -45,6 +45,20 @@ def dft_input(name):
     return siggen.noise_iq(c["seed"], c["nsamp"]) if c["kind"] == "noise" else siggen.fm_header_iq(c["seed"], c["nsamp"], c["kind"], snr_db=c["snr_db"])
 
 
+# wideband captures for the `--IQ <fq>` mode: name -> (sr_base, seconds, seed, emitters, candidate Hz list)
+_M10_TAIL = "".join("10" if b == "1" else "01" for b in "0110010010011111")
+DFT_WB_CASES = {
+    "wb2400k": (2400000, 1.0, 11, [("RS41", 300e3), ("DFM9", -500e3), ("M10", 800e3, _M10_TAIL), ("RS92", -900e3)],
+                [300e3, -500e3, 800e3, -900e3, 100e3]),
+    "wb1000k": (1000000, 1.6, 12, [("RS41", 200e3), ("LMS6", -300e3), ("IMET5", 50e3)], [200e3, -300e3, 50e3, -123456.0]),   # IF 50 kHz
+}
+
+
+def dft_wb_input(name):
+    sr, secs, seed, emit, _ = DFT_WB_CASES[name]
+    return siggen.wideband_mix(seed, int(sr * secs), sr, emit, snr_db=6.0, dc=(250.0, -150.0))
+
+
 def main():
     out = {}
     for name, (ck, _, _) in FSK_CASES.items():
@@ -67,7 +81,15 @@ def main():
         rc, dets = po.ref_cli_dft_detect(iq, 48000, 15.0, True, True)
         dj[name] = {"exit_code": rc, "dets": dets, "sha": hashlib.sha256(iq.tobytes()).hexdigest()}
     json.dump(dj, open(os.path.join(HERE, "golden_dft.json"), "w"), indent=1)
-    print("wrote golden_fsk.npz, golden_dft.json")
+    wj = {}
+    for name, (sr, _, _, _, hz) in DFT_WB_CASES.items():
+        iq = dft_wb_input(name)
+        wj[name] = {"sha": hashlib.sha256(iq.tobytes()).hexdigest(), "fq": {}}
+        for f in hz:
+            rc, dets = po.ref_cli_dft_detect(iq, sr, 15.0, True, True, fq=f / sr)     # dft_detect -v -c --IQ fq --bw 15 --dc - sr 16
+            wj[name]["fq"][repr(f)] = {"exit_code": rc, "dets": dets}
+    json.dump(wj, open(os.path.join(HERE, "golden_dft_wb.json"), "w"), indent=1)
+    print("wrote golden_fsk.npz, golden_dft.json, golden_dft_wb.json")
 
 
 if __name__ == "__main__":

@@ -77,3 +77,24 @@ def test_dft_detect_cli_matches_reference(cuda, kind, extra):
         else:
             assert a.split(":")[0] == b.split(":")[0]
             assert abs(float(a.split(":")[1].split()[0]) - float(b.split(":")[1].split()[0])) <= 2e-4
+
+
+@needs_ref
+@pytest.mark.parametrize("hz,extra", [(300e3, ["-v", "-c"]), (-500e3, []), (100e3, ["-c"]), (300e3, ["-v", "-c", "-t", "0.5"])])
+def test_dft_detect_cli_wideband_matches_reference(cuda, hz, extra):
+    """`--IQ <fq>`: same stdout lines, stderr "IF:/dec:" banner and exit code as the reference binary on a 2.4 MHz capture"""
+    sr = 2400000
+    iq = siggen.wideband_mix(21, int(sr * 1.2), sr, [("RS41", 300e3), ("DFM9", -500e3)], snr_db=6.0, dc=(200.0, 100.0))
+    args = extra + ["--IQ", repr(hz / sr), "--bw", "15", "--dc", "-", str(sr), "16"]
+    ro, re_, rrc = run(os.path.join(po.REF_DIR, "dft_detect"), args, iq.tobytes())
+    go, ge, grc = run(os.path.join(BIN, "dft_detect"), args, iq.tobytes())
+    assert grc == rrc
+    assert b"IF: 48000" in ge and b"dec: 50" in ge and b"IF: 48000" in re_
+    rl, gl = ro.decode().splitlines(), go.decode().splitlines()
+    assert len(rl) == len(gl)
+    for a, b in zip(rl, gl):
+        if a.startswith("sample:"):
+            assert a == b
+        else:
+            assert a.split(":")[0] == b.split(":")[0]
+            assert abs(float(a.split(":")[1].split()[0]) - float(b.split(":")[1].split()[0])) <= 2e-4

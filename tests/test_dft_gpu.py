@@ -102,3 +102,69 @@ def test_imet_afsk_branch_shifts_the_block_schedule(cuda):
         shifted += len(blks) < 14 * (nsamp // (b.K - 4))
     assert shifted >= 1, "the test signal no longer exercises the iMet branch"
     assert b.launches > 3          # at least one relaunch happened
+
+
+# ---- wideband mode: dft_detect --IQ <fq> --------------------------------------------------------------
+WB_SR = 2400000
+_M10_TAIL = "".join("10" if b == "1" else "01" for b in "0110010010011111")     # Manchester frame-type bits, as in build_channels
+WB_EMIT = [("RS41", 300e3), ("DFM9", -500e3), ("M10", 800e3, _M10_TAIL), ("RS92", -900e3), ("LMS6", 1000e3), ("IMET5", -50e3)]
+
+
+def _wb_capture(seed=1, secs=1.5, sr=WB_SR, snr_db=5.0, dc=(300.0, -200.0)):
+    return siggen.wideband_mix(seed, int(sr * secs), sr, WB_EMIT, snr_db=snr_db, dc=dc)
+
+
+def test_channeliser_matches_oracle_if_stream():
+    """rotate + decimating FIR output (float IQ at the IF rate) against the restated dft_detect.c:751-761 front."""
+    import torch
+    from radiosonde_auto_rx_b200.dft import DftWidebandBatch
+    wide = _wb_capture(secs=0.5)
+    fqs = np.array([300e3, -500e3, 800e3, -900e3, 123456.0, 0.0, -1199999.0, 1200000.0]) / WB_SR
+    b = DftWidebandBatch(WB_SR, 15.0, True, nchan=len(fqs))
+    assert (b.sample_rate, b.decM, b.dectaps) == (48000, 50, 343)
+    d_w = torch.from_numpy(wide).cuda()
+    nout = wide.shape[0] // b.decM
+    d_o = torch.zeros((len(fqs), nout, 2), dtype=torch.float32, device="cuda")
+    assert b.channelise(d_w, "cs16", wide.shape[0], fqs, d_o) == nout
+    got = d_o.cpu().numpy().view(np.complex64)[..., 0]
+    for c, fq in enumerate(fqs):
+        _, _, info, ref = po.dft_oracle_run_wideband(wide, WB_SR, float(fq), 15.0, True, True, want_if=True)
+        assert info["if_n"] == nout
+        err = np.abs(got[c] - ref).max()
+        assert err <= 2e-6 * max(1.0, np.abs(ref).max()), (c, fq, err)        # float32 FIR, different summation order
+
+
+@pytest.mark.parametrize("fmt", ["cs16", "f32", "cu8"])
+def test_wideband_detect_matches_oracle(fmt):
+    """type / sign / position / exit code identical, score and df within the --iq mode's tolerances, per candidate fq"""
+    from radiosonde_auto_rx_b200.dft import DftWidebandBatch
+    wide = _wb_capture(seed=3)
+    if fmt == "f32":
+        wide = (wide.astype(np.float32) / np.float32(32768.0))
+    elif fmt == "cu8":
+        wide = np.clip(np.rint(wide.astype(np.float32) / 96.0) + 128, 0, 255).astype(np.uint8)
+    hz = [e[1] for e in WB_EMIT] + [100e3, -700e3]                      # two empty frequencies
+    fqs = np.array(hz) / WB_SR
+    b = DftWidebandBatch(WB_SR, 15.0, True, nchan=len(fqs))
+    got = b.run(wide, fqs, cont=True)
+    nfound = 0
+    for c, fq in enumerate(fqs):
+        rc, dets, _, _ = po.dft_oracle_run_wideband(wide, WB_SR, float(fq), 15.0, True, True)
+        compare(got[c], rc, dets, f"{fmt} fq={fq:+.5f}")
+        nfound += len(dets) > 0
+    assert nfound >= len(WB_EMIT) - 1
+
+
+def test_wideband_odd_rate_and_time_limit():
+    """sr_base that 48000 does not divide: the IF rate walks up to the next divisor (dft_detect.c:1038-1041); -t stops early"""
+    from radiosonde_auto_rx_b200.dft import DftWidebandBatch
+    sr = 1000000                                                         # -> IF 50000, decM 20
+    wide = siggen.wideband_mix(5, int(sr * 2.5), sr, [("RS41", 200e3), ("DFM9", -300e3)], snr_db=8.0)
+    fqs = np.array([200e3, -300e3, 0.0]) / sr
+    b = DftWidebandBatch(sr, 15.0, True, nchan=3)
+    assert (b.sample_rate, b.decM) == (50000, 20)
+    for cont, tl in ((False, -1.0), (True, 1.0)):
+        got = b.run(wide, fqs, cont=cont, tl=tl)
+        for c, fq in enumerate(fqs):
+            rc, dets, _, _ = po.dft_oracle_run_wideband(wide, sr, float(fq), 15.0, True, cont, tl)
+            assert got[c][0] == rc and [(d.type, d.pos) for d in got[c][1]] == [(o[0], o[2]) for o in dets], (cont, tl, c, got[c], dets)

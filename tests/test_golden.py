@@ -15,6 +15,7 @@ from oracle import pyoracle as po                      # noqa: E402
 
 G = np.load(os.path.join(HERE, "golden_fsk.npz"))
 GD = json.load(open(os.path.join(HERE, "golden_dft.json")))
+GW = json.load(open(os.path.join(HERE, "golden_dft_wb.json")))
 
 
 @pytest.mark.parametrize("name", list(mg.FSK_CASES))
@@ -38,6 +39,37 @@ def test_dft_oracle_reproduces_golden(built, name):
     assert rc == GD[name]["exit_code"] and len(dets) == len(GD[name]["dets"])
     for a, b in zip(dets, GD[name]["dets"]):
         assert a[0] == b[0] and a[2] == b[2] and abs(a[1] - b[1]) < 1e-3 and abs(a[3] - b[3]) < 0.2
+
+
+@pytest.mark.parametrize("name", list(mg.DFT_WB_CASES))
+def test_dft_wideband_oracle_reproduces_golden(built, name):
+    """`dft_detect --IQ <fq>` (translate + decimate front) restatement against the reference binary's recorded output"""
+    iq = mg.dft_wb_input(name)
+    assert hashlib.sha256(iq.tobytes()).hexdigest() == GW[name]["sha"]
+    sr = mg.DFT_WB_CASES[name][0]
+    ndet = 0
+    for f, g in GW[name]["fq"].items():
+        rc, dets, _, _ = po.dft_oracle_run_wideband(iq, sr, float(f) / sr, 15.0, True, True)
+        assert rc == g["exit_code"] and len(dets) == len(g["dets"]), (f, rc, dets, g)
+        for a, b in zip(dets, g["dets"]):
+            assert a[0] == b[0] and a[2] == b[2] and abs(a[1] - b[1]) < 1e-3 and abs(a[3] - b[3]) < 0.2
+        ndet += len(dets)
+    assert ndet >= 3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(mg.DFT_WB_CASES))
+def test_dft_wideband_cuda_reproduces_golden(cuda, name):
+    from radiosonde_auto_rx_b200 import dft
+    iq = mg.dft_wb_input(name)
+    sr = mg.DFT_WB_CASES[name][0]
+    fs = list(GW[name]["fq"])
+    got = dft.DftWidebandBatch(sr, 15.0, True, nchan=len(fs)).run(iq, np.array([float(f) / sr for f in fs]), cont=True)
+    for (rc, dets), f in zip(got, fs):
+        g = GW[name]["fq"][f]
+        assert rc == g["exit_code"] and len(dets) == len(g["dets"]), (f, rc, dets, g)
+        for d, e in zip(dets, g["dets"]):
+            assert d.type == e[0] and d.pos == e[2] and abs(d.score - e[1]) < 2e-4 and abs(d.df_hz - e[3]) < 0.2
 
 
 @pytest.mark.gpu
