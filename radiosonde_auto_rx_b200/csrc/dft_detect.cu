@@ -101,9 +101,10 @@ struct DftParams {
 __device__ __forceinline__ float2 dft_load(const void *iq, int fmt, long long idx)
 {
     if (fmt == 1) return __ldg((const float2 *)iq + idx);
-    if (fmt == 0) { const short2 s = __ldg((const short2 *)iq + idx); return make_float2((float)((double)s.x / 32768.0), (float)((double)s.y / 32768.0)); }
+    /* x/32768.0 and (u-128)/128.0 rounded to float (:568-576) are exact power-of-two scalings of small integers: a float multiply is bit-identical */
+    if (fmt == 0) { const short2 s = __ldg((const short2 *)iq + idx); return make_float2((float)s.x * (1.0f / 32768.0f), (float)s.y * (1.0f / 32768.0f)); }
     const uchar2 u = __ldg((const uchar2 *)iq + idx);
-    return make_float2((float)(((int)u.x - 128) / 128.0), (float)(((int)u.y - 128) / 128.0));
+    return make_float2((float)((int)u.x - 128) * (1.0f / 128.0f), (float)((int)u.y - 128) * (1.0f / 128.0f));
 }
 
 /* ---- K0: mean of every block of maxcnt raw samples (IQdc, dft_detect.c:583-588); avg[i+1] applies to block i+1 ---- */
@@ -134,6 +135,7 @@ __global__ void dft_dcavg_kernel(const DftParams p)
  *          (dft_detect.c:751-761 with the tables of :1021-1111).  One CTA = one channel x CH_TM outputs; the rotated window is
  *          staged once in shared memory, each warp then forms whole outputs (lanes stride the taps, conflict-free float2 reads). */
 #define CH_THREADS 256
+#define CH_OW 4                                  /* outputs a warp accumulates together (shared coefficient load, 8 independent FMA chains) */
 struct ChanParams {
     const void *wide; int fmt; long long nwide;
     const float2 *wavg; int wmaxcnt;          /* IQdc means of the wide stream (maxcnt = IF_sr/32*decM, :1155-1156) */
@@ -145,7 +147,7 @@ struct ChanParams {
 
 /* (cos,sin)(t*2*pi) for the LUT entry ex[n], t = f0*n, formed like the reference's cexp(t*2*M_PI*I) (:1100): the double argument is
  * reduced with a three-term 2*pi (FMA keeps each product exact), then the fast-path sincos. */
-__device__ __forceinline__ float2 lut_entry(double f0, int n)
+__device__ __forceinline__ double2 lut_cs(double f0, int n)
 {
     const double t = f0 * (double)n;
     const double arg = (t * 2) * M_PI;
@@ -155,7 +157,7 @@ __device__ __forceinline__ float2 lut_entry(double f0, int n)
     r = fma(-k, -5.989539619436679332e-33, r);
     double sn, cs;
     sincos(r, &sn, &cs);
-    return make_float2((float)cs, (float)sn);
+    return make_double2(cs, sn);
 }
 
 __global__ void __launch_bounds__(CH_THREADS) dft_chan_kernel(const ChanParams q)
@@ -165,30 +167,67 @@ __global__ void __launch_bounds__(CH_THREADS) dft_chan_kernel(const ChanParams q
     const long long m0 = (long long)blockIdx.x * q.TM;
     const int tm = (int)min((long long)q.TM, q.nout - m0);
     const int W = (tm - 1) * decM + taps;
-    float *wsm = (float *)(xs + (q.TM - 1) * decM + taps);
+    float *wsm = (float *)(xs + q.TM * decM + taps);               /* (window padded by one decM row) */
     const long long g0 = m0 * decM + decM - taps;                /* wide index of xs[0]; output m ends at wide sample m*decM+decM-1 */
     const double f0 = q.f0[c];
     for (int i = threadIdx.x; i < taps; i += CH_THREADS) wsm[i] = q.ws[i];
-    for (int i = threadIdx.x; i < W; i += CH_THREADS) {
-        const long long g = g0 + i;
-        float2 v = make_float2(0.f, 0.f);
-        if (g >= 0) {
-            const float2 r = dft_load(q.wide, q.fmt, g);
-            const float2 a = q.wavg[g / q.wmaxcnt];
-            const float x = r.x - a.x, y = r.y - a.y;                                  /* :627-628 */
-            const float2 e = lut_entry(f0, (int)(g % q.lut_len));
-            v = make_float2(x * e.x - y * e.y, x * e.y + y * e.x);                     /* decMbuf[j]*ex[] (:755) */
-        }
-        xs[i] = v;
+    /* Rotation: thread t owns window samples ib+t, ib+t+256, ...  Its LUT index advances by 256 (mod lut_len) per step, so after one full
+       evaluation the entry is carried by a double-precision angle addition (error ~1e-16 per step, < 60 steps; the value is then rounded to
+       float like the table).  On a LUT wrap it is re-evaluated, which also reproduces the table's phase jump when freq0 is not a multiple
+       of the divisor d (:1082-1091 may leave it unsnapped).  64-bit divisions happen once per thread, not per sample. */
+    const long long gb = g0 < 0 ? 0 : g0;
+    const int ib = (int)(gb - g0);
+    for (int i = threadIdx.x; i < ib; i += CH_THREADS) xs[i] = make_float2(0.f, 0.f);       /* before the stream: the calloc'ed ring (:1104) */
+    for (int i = W + threadIdx.x; i < q.TM * decM + taps; i += CH_THREADS) xs[i] = make_float2(0.f, 0.f);
+    const bool carry = q.lut_len > 2 * CH_THREADS;
+    const double2 st = lut_cs(f0, CH_THREADS);                   /* e^{j 2 pi f0 256} */
+    long long gq = (gb + threadIdx.x) / q.wmaxcnt;               /* DC-block index of this thread's sample ... */
+    int gr = (int)((gb + threadIdx.x) % q.wmaxcnt);              /* ... and position inside that block */
+    int n = (int)((gb + threadIdx.x) % q.lut_len);
+    double2 e = lut_cs(f0, n);
+    int i = ib + threadIdx.x;
+    float2 rn = i < W ? dft_load(q.wide, q.fmt, g0 + i) : make_float2(0.f, 0.f);
+    for (; i < W; i += CH_THREADS) {
+        const float2 r = rn;
+        if (i + CH_THREADS < W) rn = dft_load(q.wide, q.fmt, g0 + i + CH_THREADS);     /* next sample in flight while this one is rotated */
+        const float2 a = q.wavg[gq];
+        const float x = r.x - a.x, y = r.y - a.y;                                      /* :627-628 */
+        const float ex = (float)e.x, ey = (float)e.y;
+        xs[i] = make_float2(x * ex - y * ey, x * ey + y * ex);                         /* decMbuf[j]*ex[] (:755) */
+        gr += CH_THREADS; while (gr >= q.wmaxcnt) { gr -= q.wmaxcnt; ++gq; }
+        n += CH_THREADS;
+        if (carry && n < q.lut_len) e = make_double2(e.x * st.x - e.y * st.y, e.x * st.y + e.y * st.x);
+        else { n %= q.lut_len; e = lut_cs(f0, n); }
     }
     __syncthreads();
+    float2 *out = q.out + (long long)c * q.out_stride + m0;
+    /* FIR: a warp forms CH_OW consecutive outputs at a time; lanes stride the taps (consecutive float2 words: conflict-free), one
+       coefficient load feeds 2*CH_OW independent FMA chains.  Outputs past tm read the zero-filled pad and are not stored. */
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int o = warp; o < tm; o += CH_THREADS / 32) {
+    for (int o = warp * CH_OW; o < tm; o += (CH_THREADS / 32) * CH_OW) {
         const float2 *xp = xs + o * decM;
-        float ax = 0.f, ay = 0.f;
-        for (int i = lane; i < taps; i += 32) { const float w = wsm[i]; const float2 v = xp[i]; ax = fmaf(w, v.x, ax); ay = fmaf(w, v.y, ay); }
-        for (int d = 16; d; d >>= 1) { ax += __shfl_xor_sync(0xffffffffu, ax, d); ay += __shfl_xor_sync(0xffffffffu, ay, d); }
-        if (lane == 0) q.out[(long long)c * q.out_stride + m0 + o] = make_float2(ax, ay);
+        const bool full = o + CH_OW <= tm;
+        float ax[CH_OW], ay[CH_OW];
+#pragma unroll
+        for (int u = 0; u < CH_OW; ++u) { ax[u] = 0.f; ay[u] = 0.f; }
+        if (full) {
+            for (int k = lane; k < taps; k += 32) {
+                const float w = wsm[k];
+#pragma unroll
+                for (int u = 0; u < CH_OW; ++u) { const float2 v = xp[u * decM + k]; ax[u] = fmaf(w, v.x, ax[u]); ay[u] = fmaf(w, v.y, ay[u]); }
+            }
+        } else {
+            for (int k = lane; k < taps; k += 32) {
+                const float w = wsm[k];
+#pragma unroll
+                for (int u = 0; u < CH_OW; ++u) if (o + u < tm) { const float2 v = xp[u * decM + k]; ax[u] = fmaf(w, v.x, ax[u]); ay[u] = fmaf(w, v.y, ay[u]); }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < CH_OW; ++u) {
+            for (int d = 16; d; d >>= 1) { ax[u] += __shfl_xor_sync(0xffffffffu, ax[u], d); ay[u] += __shfl_xor_sync(0xffffffffu, ay[u], d); }
+            if (lane == 0 && o + u < tm) out[o + u] = make_float2(ax[u], ay[u]);
+        }
     }
 }
 
@@ -833,10 +872,11 @@ extern "C" int b200dft_create_wideband(b200dft_t **out, int sr_base, double bw_k
     int maxsmem = 0;
     CK(cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     int tm = 64;                                                                   /* outputs per CTA: window <= ~96 KB */
-    while (tm > 1 && ((size_t)(tm - 1) * decM + taps) * sizeof(float2) > 96 * 1024) tm >>= 1;
-    h->ch_tm = tm; h->ch_smem = ((size_t)(tm - 1) * decM + taps) * sizeof(float2) + (size_t)taps * sizeof(float) + 16;
+    while (tm > 1 && ((size_t)tm * decM + taps) * sizeof(float2) > 100 * 1024) tm >>= 1;
+    h->ch_tm = tm; h->ch_smem = ((size_t)tm * decM + taps) * sizeof(float2) + (size_t)taps * sizeof(float) + 16;
     if (h->ch_smem + 1024 > (size_t)maxsmem) { b200dft_destroy(h); *out = 0; return fail(B200DFT_EINVAL, "decimation filter does not fit shared memory"); }
-    CK(cudaFuncSetAttribute(dft_chan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsmem));
+    {   cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, (const void *)dft_chan_kernel));
+        CK(cudaFuncSetAttribute(dft_chan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsmem - (int)fa.sharedSizeBytes)); }
     CK(cudaMalloc(&h->d_ws_dec, ws.size() * 4)); CK(cudaMemcpy(h->d_ws_dec, ws.data(), (size_t)taps * 4, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&h->d_f0, sizeof(double) * nchan));
     for (int i = 0; i < 2; i++) CK(cudaEventCreate(&h->evc[i]));
