@@ -141,10 +141,21 @@ typedef struct {
     float score;                       /* header correlation                                                                    */
     unsigned char bytes[518];          /* de-whitened frame (bytes 0..7: header)                                                */
     float bytescore[518];              /* soft bit of smallest magnitude per byte (input of the reference's ecc3/4 erasure logic) */
+    int   ec;                          /* ecc > 0: rs41_ecc() result: corrected symbols, or -1 / -2 / -3 = word 1 / word 2 / both failed    */
+    int   crc_mask;                    /* ecc > 0: bit k = check_CRC() == 0 for block k of 7928 FRAME, 7A2A PTU, 7C1E GPS1, 7D59 GPS2,   */
+                                       /*          7B15 GPS3, 76xx ZERO at their standard positions (rs41mod.c:307-319, 338-392)       */
 } b200fsk_rs41_frame_t;
 int  b200fsk_rs41_framesync_device(const float *d_soft, long stride, const int *d_nbits, int nbits, int nchan, int softinv, int inv,
                                    b200fsk_rs41_frame_t *h_frames, int max_frames, int *nframes, int device, void *stream);
+/* the same with rs41mod's Reed-Solomon stage applied to every frame before it is returned (rs41_ecc,
+ * demod/mod/rs41mod.c:1703-1976; decoder demod/mod/bch_ecc_mod.c:877-966).  ecc = 0: none (identical to the call above),
+ * 1: `--ecc` (rs41mod's default), 2: `--ecc2`, which `--json` selects (rs41mod.c:2703-2706) -- the level auto_rx runs at
+ * (auto_rx/autorx/decode.py:909).  bytes[] then holds the corrected frame, exactly what `rs41mod -r` prints. */
+int  b200fsk_rs41_frames_device(const float *d_soft, long stride, const int *d_nbits, int nbits, int nchan, int softinv, int inv, int ecc,
+                                b200fsk_rs41_frame_t *h_frames, int max_frames, int *nframes, int device, void *stream);
 const char *b200fsk_framesync_last_error(void);
+/* device time (ms, CUDA events) of the frame-sync kernel in this thread's most recent call; < 0 if none */
+float b200fsk_framesync_last_kernel_ms(void);
 
 /* kernel launches issued by this handle so far (bench.py's gpu_launches) */
 long b200fsk_launch_count(const b200fsk_t *h);

@@ -339,27 +339,90 @@ def ref_cli_dft_detect(iq: np.ndarray, sample_rate: int = 48000, bw_khz: float =
 # ------------------------------------------------------------------------------------------------
 class SsoFrame(C.Structure):
     _fields_ = [("len", C.c_int), ("nbytes_read", C.c_int), ("first_bit", C.c_long), ("score", C.c_float),
-                ("bytes", C.c_ubyte * 518), ("bytescore", C.c_float * 518)]
+                ("bytes", C.c_ubyte * 518), ("bytescore", C.c_float * 518), ("ec", C.c_int), ("crc_mask", C.c_int)]
 
 
-def softsync_oracle(soft: np.ndarray, softinv: bool = False, inv: bool = True):
+def softsync_oracle(soft: np.ndarray, softinv: bool = False, inv: bool = True, ecc: int = 0):
     """-> [(len, first_bit, score, bytes[len] as numpy uint8)] like `rs41mod --softin -i -r` would print."""
     L = lib()
     L.sso_rs41.restype = C.c_int
-    L.sso_rs41.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    L.sso_rs41.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
     soft = np.ascontiguousarray(soft, dtype=np.float32)
     cap = soft.size // 4000 + 4
     fr = (SsoFrame * cap)()
-    n = L.sso_rs41(soft.ctypes.data, soft.size, int(softinv), int(inv), fr, cap)
-    return [(f.len, f.first_bit, f.score, np.frombuffer(bytes(f.bytes), np.uint8)[: f.len].copy(), f.nbytes_read) for f in fr[: min(n, cap)]]
+    n = L.sso_rs41(soft.ctypes.data, soft.size, int(softinv), int(inv), int(ecc), fr, cap)
+    return [(f.len, f.first_bit, f.score, np.frombuffer(bytes(f.bytes), np.uint8)[: f.len].copy(), f.nbytes_read, f.ec, f.crc_mask) for f in fr[: min(n, cap)]]
 
 
-def ref_cli_rs41mod_raw(soft_bytes: bytes, inv: bool = True):
-    """Run oracle/_ref/rs41mod -r --softin [-i] -> [(hex string, tag)] per printed frame."""
+def ref_cli_rs41mod_raw(soft_bytes: bytes, inv: bool = True, ecc: int = 1):
+    """Run oracle/_ref/rs41mod -r [--ecc2] --softin [-i] -> [(hex string, tag)] per printed frame; tag = "[OK] (n)" / "[NO] (-+)"."""
     exe = os.path.join(REF_DIR, "rs41mod")
-    r = subprocess.run([exe, "-r", "--softin"] + (["-i"] if inv else []), input=soft_bytes, capture_output=True)
+    r = subprocess.run([exe, "-r"] + (["--ecc2"] if ecc == 2 else []) + ["--softin"] + (["-i"] if inv else []), input=soft_bytes, capture_output=True)
     out = []
     for ln in r.stdout.decode().splitlines():
         parts = ln.split(" ", 1)
         out.append((parts[0], parts[1] if len(parts) > 1 else ""))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Reed-Solomon stage of rs41mod (SURVEY 8f-4)
+# ------------------------------------------------------------------------------------------------
+def _ecc_lib():
+    L = lib()
+    L.ecco_rs255_encode.argtypes = [C.c_void_p]
+    L.ecco_rs255_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ecco_rs41_ecc.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.ecco_crc16.argtypes = [C.c_void_p, C.c_int]
+    L.ecco_rs41_check_crc.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    return L
+
+
+def rs255_encode(msg: np.ndarray) -> np.ndarray:
+    """msg: 231 bytes -> codeword of 255 bytes (parity in cw[0:24], message in cw[24:])."""
+    cw = np.zeros(255, np.uint8)
+    cw[24:] = msg
+    _ecc_lib().ecco_rs255_encode(cw.ctypes.data)
+    return cw
+
+
+def rs255_decode(cw: np.ndarray):
+    """-> (return code, corrected copy)"""
+    c = np.ascontiguousarray(cw, dtype=np.uint8).copy()
+    return _ecc_lib().ecco_rs255_decode(c.ctypes.data, None, None), c
+
+
+def rs41_ecc(frame: np.ndarray, frmlen: int, level: int = 2):
+    f = np.zeros(518, np.uint8)
+    f[: frame.size] = frame
+    return _ecc_lib().ecco_rs41_ecc(f.ctypes.data, frmlen, level), f
+
+
+def crc16(data: bytes) -> int:
+    b = np.frombuffer(bytes(data), np.uint8)
+    return _ecc_lib().ecco_crc16(b.ctypes.data, b.size)
+
+
+_bch = None
+
+
+def ref_rs255():
+    """The reference module itself (oracle/_ref/libbch_ref.so): (encode(cw), decode(cw) -> (rc, cw))."""
+    global _bch
+    if _bch is None:
+        L = _load(os.path.join(REF_DIR, "libbch_ref.so"))
+        rs = (C.c_ubyte * 4096)()                         # RS_t: 7 + 255 + GF_t(4+4+1+256+256) bytes, generously
+        L.rs_init_RS255(rs)
+        _bch = (L, rs)
+    L, rs = _bch
+
+    def enc(cw):
+        c = np.ascontiguousarray(cw, dtype=np.uint8).copy()
+        L.rs_encode(rs, c.ctypes.data_as(C.c_void_p))
+        return c
+
+    def dec(cw):
+        c = np.ascontiguousarray(cw, dtype=np.uint8).copy()
+        ep, ev = (C.c_ubyte * 32)(), (C.c_ubyte * 32)()
+        return L.rs_decode(rs, c.ctypes.data_as(C.c_void_p), ep, ev), c
+    return enc, dec

@@ -6,7 +6,8 @@
  * (demod/mod/rs41mod.c:2875-2960: polarity rule, bit inversion, little-endian bytes, XOR de-whitening mask, per-byte
  * minimum soft score, frame length from the frame-type byte :407-415, :2483-2491).  SURVEY.md §8f-1.
  * Pinned by tests/test_softsync.py against `oracle/_ref/rs41mod -r --softin -i` (raw frame hex of frames the
- * Reed-Solomon stage leaves untouched).  The RS/BCH ECC and telemetry parsing are NOT restated.
+ * Reed-Solomon stage leaves untouched); with ecc > 0 the Reed-Solomon stage of oracle/ecc_oracle.c runs in the same
+ * frame buffer (tests/test_ecc.py).  Telemetry parsing is NOT restated.
  */
 #include "oracle.h"
 #include <math.h>
@@ -28,7 +29,7 @@ static const unsigned char RS41_MASK[64] = {                                    
 
 /* soft: nbits float soft decisions of one channel; softinv = --softinv (negate on read), inv = -i (gpx.option.inv).
  * Returns the number of frames; frames[k] receives length, position of the first payload bit, header score, bytes, scores. */
-int sso_rs41(const float *soft, long nbits, int softinv, int inv, sso_frame_t *frames, int maxframes)
+int sso_rs41(const float *soft, long nbits, int softinv, int inv, int ecc, sso_frame_t *frames, int maxframes)
 {
     float sbuf[HEADLEN]; int bufpos = -1, nf = 0; long pos = 0;
     unsigned char frame[FRAME_LEN]; float bytescore[FRAME_LEN];
@@ -72,9 +73,15 @@ int sso_rs41(const float *soft, long nbits, int softinv, int inv, sso_frame_t *f
         if (byte_count < POS_GPS1) for (int i = byte_count; i < FRAME_LEN; i++) frame[i] = 0;
         int ft = 0; unsigned char b = frame[POS_FRAME - 1];
         for (int i = 0; i < 4; i++) ft += ((b >> i) & 1) - ((b >> (i + 4)) & 1);
+        int ec = 0, crcm = 0;
+        if (ecc > 0) {
+            static const int bpos[6] = {0x039, 0x065, 0x093, 0x0B5, 0x112, 0x12B}, bpck[6] = {0x7928, 0x7A2A, 0x7C1E, 0x7D59, 0x7B15, 0x7600};
+            ec = ecco_rs41_ecc(frame, ft >= 0 ? NDATA_LEN : FRAME_LEN, ecc);     /* print_frame: ec = rs41_ecc(gpx, len) (rs41mod.c:2525-2527) */
+            for (int k = 0; k < 6; k++) if (ecco_rs41_check_crc(frame, bpos[k], bpck[k]) == 0) crcm |= 1 << k;
+        }
         if (nf < maxframes) {
             sso_frame_t *f = &frames[nf];
-            f->len = ft >= 0 ? NDATA_LEN : FRAME_LEN; f->first_bit = first; f->score = mv; f->nbytes_read = byte_count;
+            f->len = ft >= 0 ? NDATA_LEN : FRAME_LEN; f->first_bit = first; f->score = mv; f->nbytes_read = byte_count; f->ec = ec; f->crc_mask = crcm;
             memcpy(f->bytes, frame, FRAME_LEN); memcpy(f->bytescore, bytescore, sizeof bytescore);
         }
         nf++;

@@ -7,6 +7,12 @@
  * accumulation like the reference), the first hit wins, the following 4080 soft bits are packed into 510 bytes
  * (little-endian bits, XOR de-whitening mask, per-byte minimum-magnitude soft score), then the scan resumes with the
  * ring exactly as the reference leaves it (frame payload bits never enter the header ring).
+ *
+ * with ecc = 1|2 the warp also runs rs41mod's Reed-Solomon stage on the frame while it is still in shared
+ * memory (rs41_ecc, demod/mod/rs41mod.c:1703-1976 for --ecc / --ecc2; decoder demod/mod/bch_ecc_mod.c:877-966): two
+ * interleaved RS(255,231) words over GF(2^8)/0x11D.  Syndromes (24 lanes, Horner), root search and Forney values (all lanes)
+ * are warp-parallel; the short Euclidean key-equation recursion runs on one lane.  The correction is applied in the running
+ * frame buffer like gpx->frame, then the six standard blocks' CRC-16 are checked (check_CRC, rs41mod.c:284-319).
  */
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -33,15 +39,171 @@ static const unsigned char RS41_MASK[64] = {
     0xD0, 0xBC, 0xB4, 0xB6, 0x06, 0xAA, 0xF4, 0x23, 0x78, 0x6E, 0x3B, 0xAE, 0xBF, 0x7B, 0x4C, 0xC1};
 
 struct SsParams {
-    const float *soft; long long stride; const int *nbits_c; int nbits; int nchan, softinv, inv, maxpc;
+    const float *soft; long long stride; const int *nbits_c; int nbits; int nchan, softinv, inv, maxpc, ecc;
     b200fsk_rs41_frame_t *frames; int *counts;
 };
+
+/* ---- GF(2^8) f = 0x11D, alpha = 2 (bch_ecc_mod.c:55-59): exp table doubled so products need no modulo -------------------- */
+#define RS_N 255
+#define RS_R 24
+#define RS_K 231
+#define RS_T 12
+#define RS_PLEN 32
+struct GfTab { unsigned char ex[512]; unsigned char lg[256]; };
+__device__ __forceinline__ unsigned gmul(const GfTab &g, unsigned a, unsigned b) { return (a && b) ? g.ex[g.lg[a] + g.lg[b]] : 0u; }
+__device__ __forceinline__ unsigned ginv(const GfTab &g, unsigned a) { return a ? g.ex[255 - g.lg[a]] : 0u; }
+__device__ __forceinline__ int pdeg(const unsigned char *p) { int d = RS_PLEN - 1; while (d >= 0 && p[d] == 0) --d; return d; }
+__device__ __forceinline__ unsigned peval(const GfTab &g, const unsigned char *p, int n, unsigned x)
+{
+    unsigned y = 0;
+    for (int i = n - 1; i >= 0; --i) y = gmul(g, y, x) ^ p[i];
+    return y;
+}
+
+struct RsScratch { unsigned char S[RS_PLEN], r0[RS_PLEN], r1[RS_PLEN], s0[RS_PLEN], s1[RS_PLEN], q[RS_PLEN], t2[RS_PLEN], dLa[RS_PLEN]; int dL, dO, status; };
+
+/* rs_decode (bch_ecc_mod.c:877-966, no erasures) by one warp on a codeword in shared memory.  Returns (uniformly) the number of
+ * corrected symbols or -1/-2/-3 with cw untouched. */
+__device__ int rs255_decode_warp(const GfTab &g, unsigned char *cw, RsScratch &w, int lane)
+{
+    unsigned sy = 0;
+    if (lane < RS_R) {                                                       /* S_i = cw(alpha^i), i = 0..23 (:638-651) */
+        const unsigned x = g.ex[lane];
+        for (int n = RS_N - 1; n >= 0; --n) sy = gmul(g, sy, x) ^ cw[n];
+        w.S[lane] = (unsigned char)sy;
+    } else w.S[lane] = 0;
+    if (!__ballot_sync(0xffffffffu, sy != 0)) return 0;
+    __syncwarp();
+    if (lane == 0) {
+        /* key equation S*Lambda = Omega mod X^24: remainder sequence of (X^24, S) with cofactors (0, 1), stopped at deg r < t
+           (polyGF_lfsr :547-582; its first step only swaps the start pair) */
+        for (int i = 0; i < RS_PLEN; ++i) { w.r0[i] = 0; w.r1[i] = w.S[i]; w.s0[i] = 0; w.s1[i] = 0; }
+        w.r0[RS_R] = 1; w.s1[0] = 1;
+        while (pdeg(w.r1) >= RS_T) {
+            const int dq = pdeg(w.r1); int dp = pdeg(w.r0);
+            for (int i = 0; i < RS_PLEN; ++i) w.q[i] = 0;
+            const unsigned lead = ginv(g, w.r1[dq]);
+            while (dp >= dq) {
+                const unsigned c = gmul(g, w.r0[dp], lead);
+                w.q[dp - dq] = (unsigned char)c;
+                for (int i = 0; i <= dq; ++i) w.r0[dp - i] ^= (unsigned char)gmul(g, w.r1[dq - i], c);
+                dp = pdeg(w.r0);
+            }
+            for (int i = 0; i < RS_PLEN; ++i) { const unsigned char t = w.r0[i]; w.r0[i] = w.r1[i]; w.r1[i] = t; w.t2[i] = w.s0[i]; }
+            const int ds = pdeg(w.s1), dqq = pdeg(w.q);
+            for (int i = 0; i <= dqq; ++i) for (int j = 0; j <= ds; ++j) if (i + j < RS_PLEN) w.t2[i + j] ^= (unsigned char)gmul(g, w.q[i], w.s1[j]);
+            for (int i = 0; i < RS_PLEN; ++i) { w.s0[i] = w.s1[i]; w.s1[i] = w.t2[i]; }
+        }
+        const int dL = pdeg(w.s1), dO = pdeg(w.r1);                          /* Lambda = s1, Omega = r1 */
+        int st = 1;
+        if (dO >= dL) st = -3;                                               /* :911-914 */
+        else if (w.s1[0] == 0) st = -2;                                      /* :915-925 */
+        else {
+            const unsigned gi = ginv(g, w.s1[0]);
+            for (int i = 0; i <= dL; ++i) w.s1[i] = (unsigned char)gmul(g, w.s1[i], gi);
+            for (int i = 0; i <= dO; ++i) w.r1[i] = (unsigned char)gmul(g, w.r1[i], gi);
+            for (int i = 0; i < RS_PLEN; ++i) w.dLa[i] = 0;
+            for (int i = 1; i <= dL; ++i) if (i & 1) w.dLa[i - 1] = w.s1[i];  /* formal derivative (:584-594) */
+        }
+        w.dL = dL; w.dO = dO; w.status = st;
+    }
+    __syncwarp();
+    if (w.status < 0) return w.status;
+    const int dL = w.dL;
+    unsigned roots = 0;                                                       /* lane tests x = lane+1, lane+33, ... (:933-946) */
+    for (int k = 0; k < 8; ++k) { const int x = lane + 1 + 32 * k; if (x < 256 && peval(g, w.s1, dL + 1, x) == 0) roots |= 1u << k; }
+    int nerr = __popc(roots);
+    for (int o = 16; o; o >>= 1) nerr += __shfl_xor_sync(0xffffffffu, nerr, o);
+    if (nerr < dL) return -1;                                                 /* :949 */
+    for (int k = 0; k < 8; ++k) if (roots >> k & 1) {
+        const unsigned x = lane + 1 + 32 * k, x1 = ginv(g, x);
+        const unsigned wv = peval(g, w.r1, w.dO + 1, x), z = peval(g, w.dLa, dL + 1, x);
+        const unsigned val = z ? gmul(g, x1, gmul(g, wv, ginv(g, z))) : 0u;   /* b == 0: Y = x^-1 Omega(x)/Lambda'(x) (:596-612) */
+        cw[g.lg[x1] % 255] ^= (unsigned char)val;
+    }
+    __syncwarp();
+    return nerr;
+}
+
+/* rs41_ecc (rs41mod.c:1703-1976), option.ecc = level (1|2), on the frame in shared memory */
+__device__ int rs41_ecc_warp(const GfTab &g, unsigned char *frame, int frmlen, int level, unsigned char *cw1, unsigned char *cw2, RsScratch &w, int lane)
+{
+    for (int i = frmlen + lane; i < SS_FRAME_LEN; i += 32) frame[i] = 0;     /* 0-padding (:1726) */
+    __syncwarp();
+    for (int i = lane; i < RS_N; i += 32) {
+        cw1[i] = i < RS_R ? frame[8 + i] : frame[56 + 2 * (i - RS_R)];
+        cw2[i] = i < RS_R ? frame[8 + RS_R + i] : frame[56 + 2 * (i - RS_R) + 1];
+    }
+    __syncwarp();
+    int e1 = rs255_decode_warp(g, cw1, w, lane); __syncwarp();
+    int e2 = rs255_decode_warp(g, cw2, w, lane); __syncwarp();
+    if (level >= 2 && (e1 < 0 || e2 < 0)) {                                   /* 2nd pass (:1738-1762) */
+        if (lane == 0) {
+            const int idpos[5] = {0x039, 0x065, 0x093, 0x0B5, 0x112}, idpck[5] = {0x7928, 0x7A2A, 0x7C1E, 0x7D59, 0x7B15};
+            for (int k = 0; k < 5; ++k) { frame[idpos[k]] = (idpck[k] >> 8) & 0xFF; frame[idpos[k] + 1] = idpck[k] & 0xFF; }
+        }
+        __syncwarp();
+        const unsigned char b = frame[SS_POS_FRAME - 1]; int ft = 0;
+        for (int i = 0; i < 4; ++i) ft += ((b >> i) & 1) - ((b >> (i + 4)) & 1);
+        if (ft < -2) { for (int i = SS_NDATA_LEN + 7 + lane; i < SS_FRAME_LEN - 2; i += 32) frame[i] = 0; }
+        else {
+            for (int i = SS_NDATA_LEN + lane; i < SS_FRAME_LEN; i += 32) frame[i] = 0;
+            for (int i = 0x12B + 2 + lane; i < SS_NDATA_LEN - 2; i += 32) frame[i] = 0;
+            if (lane == 0) { frame[0x12B] = 0x76; frame[0x12B + 1] = 0x11; frame[SS_NDATA_LEN - 2] = 0xEC; frame[SS_NDATA_LEN - 1] = 0xC7; }
+        }
+        __syncwarp();
+        for (int i = RS_R + lane; i < RS_N; i += 32) { cw1[i] = frame[56 + 2 * (i - RS_R)]; cw2[i] = frame[56 + 2 * (i - RS_R) + 1]; }   /* parity part as pass 1 left it */
+        __syncwarp();
+        e1 = rs255_decode_warp(g, cw1, w, lane); __syncwarp();
+        e2 = rs255_decode_warp(g, cw2, w, lane); __syncwarp();
+    }
+    for (int i = lane; i < RS_N; i += 32) {                                   /* write-back (:1952-1959) */
+        if (i < RS_R) { frame[8 + i] = cw1[i]; frame[8 + RS_R + i] = cw2[i]; }
+        else { frame[56 + 2 * (i - RS_R)] = cw1[i]; frame[56 + 2 * (i - RS_R) + 1] = cw2[i]; }
+    }
+    __syncwarp();
+    if (e1 < 0 || e2 < 0) return -((e1 < 0 ? 1 : 0) | (e2 < 0 ? 2 : 0));
+    return e1 + e2;
+}
+
+/* check_CRC (rs41mod.c:307-319) of block k of the standard frame layout; lanes 0..5 -> bit k of the result = CRC ok */
+__device__ unsigned rs41_crc_mask_warp(const unsigned char *frame, int lane)
+{
+    const int bpos[6] = {0x039, 0x065, 0x093, 0x0B5, 0x112, 0x12B}, btyp[6] = {0x79, 0x7A, 0x7C, 0x7D, 0x7B, 0x76};
+    int ok = 0;
+    if (lane < 6) {
+        const int pos = bpos[lane];
+        if (frame[pos] == btyp[lane]) {
+            const int len = frame[pos + 1];
+            if (pos + len + 4 <= SS_FRAME_LEN) {
+                int rem = 0xFFFF;
+                for (int i = 0; i < len; ++i) {
+                    rem ^= frame[pos + 2 + i] << 8;
+                    for (int j = 0; j < 8; ++j) rem = (rem & 0x8000) ? ((rem << 1) ^ 0x1021) & 0xFFFF : (rem << 1) & 0xFFFF;
+                }
+                ok = rem == (frame[pos + 2 + len] | (frame[pos + 3 + len] << 8));
+            }
+        }
+    }
+    return __ballot_sync(0xffffffffu, ok) & 0x3Fu;
+}
 
 __global__ void __launch_bounds__(SS_WARPS * 32) rs41_framesync_kernel(const SsParams p)
 {
     __shared__ float s_w[SS_WARPS][96];
     __shared__ unsigned char s_frame[SS_WARPS][SS_FRAME_LEN + 2];
     __shared__ float s_score[SS_WARPS][SS_FRAME_LEN];
+    __shared__ GfTab s_gf;
+    __shared__ unsigned char s_cw[SS_WARPS][2][256];
+    __shared__ RsScratch s_rs[SS_WARPS];
+    if (p.ecc > 0) {                                                          /* exp / log tables (GF_genTab, bch_ecc_mod.c:136-170) */
+        if (threadIdx.x == 0) {
+            unsigned b = 1;
+            for (int i = 0; i < 255; ++i) { s_gf.ex[i] = s_gf.ex[i + 255] = (unsigned char)b; s_gf.lg[b] = (unsigned char)i; b <<= 1; if (b & 0x100) b ^= 0x11D; }
+            s_gf.ex[510] = s_gf.ex[0]; s_gf.ex[511] = s_gf.ex[1]; s_gf.lg[0] = 0;
+        }
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5, c = blockIdx.x * SS_WARPS + wp;
     if (c >= p.nchan) return;
     float *w = s_w[wp]; unsigned char *frame = s_frame[wp]; float *score = s_score[wp];
@@ -97,14 +259,20 @@ __global__ void __launch_bounds__(SS_WARPS * 32) rs41_framesync_kernel(const SsP
         __syncwarp();
         const int byte_count = SS_FRAMESTART + nby;
         if (byte_count < SS_POS_GPS1) { for (int i = byte_count + lane; i < SS_FRAME_LEN; i += 32) frame[i] = 0; __syncwarp(); }   /* print_frame :2481-2484 */
+        int flen, ec = 0; unsigned crc = 0;
+        {
+            const unsigned char b = frame[SS_POS_FRAME - 1]; int ft = 0;
+            for (int i = 0; i < 4; ++i) ft += ((b >> i) & 1) - ((b >> (i + 4)) & 1);       /* frametype (rs41mod.c:407-415) */
+            flen = ft >= 0 ? SS_NDATA_LEN : SS_FRAME_LEN;
+        }
+        if (p.ecc > 0) {                                                      /* print_frame: ec = rs41_ecc(gpx, len) (rs41mod.c:2525-2527) */
+            ec = rs41_ecc_warp(s_gf, frame, flen, p.ecc, s_cw[wp][0], s_cw[wp][1], s_rs[wp], lane);
+            crc = rs41_crc_mask_warp(frame, lane);
+        }
         if (nf < p.maxpc) {
             b200fsk_rs41_frame_t *o = p.frames + (long long)c * p.maxpc + nf;
             for (int i = lane; i < SS_FRAME_LEN; i += 32) { o->bytes[i] = frame[i]; o->bytescore[i] = score[i]; }
-            if (lane == 0) {
-                const unsigned char b = frame[SS_POS_FRAME - 1]; int ft = 0;
-                for (int i = 0; i < 4; ++i) ft += ((b >> i) & 1) - ((b >> (i + 4)) & 1);   /* frametype (rs41mod.c:407-415) */
-                o->chan = c; o->len = ft >= 0 ? SS_NDATA_LEN : SS_FRAME_LEN; o->nbytes_read = byte_count; o->first_bit = first; o->score = mvf;
-            }
+            if (lane == 0) { o->chan = c; o->len = flen; o->nbytes_read = byte_count; o->first_bit = first; o->score = mvf; o->ec = ec; o->crc_mask = (int)crc; }
         }
         ++nf;
         {   /* the header ring is untouched by the payload: it still ends at the hit bit */
@@ -120,13 +288,24 @@ __global__ void __launch_bounds__(SS_WARPS * 32) rs41_framesync_kernel(const SsP
 }
 
 static thread_local char g_sserr[256];
+static thread_local float g_ss_ms = -1.0f;
+extern "C" float b200fsk_framesync_last_kernel_ms(void) { return g_ss_ms; }
 extern "C" const char *b200fsk_framesync_last_error(void) { return g_sserr; }
 #define SCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(g_sserr, sizeof g_sserr, "%s: %s", #call, cudaGetErrorString(e_)); return B200FSK_ECUDA; } } while (0)
+
+extern "C" int b200fsk_rs41_frames_device(const float *d_soft, long stride, const int *d_nbits, int nbits, int nchan, int softinv, int inv, int ecc,
+                                          b200fsk_rs41_frame_t *h_frames, int max_frames, int *nframes, int device, void *stream);
 
 extern "C" int b200fsk_rs41_framesync_device(const float *d_soft, long stride, const int *d_nbits, int nbits, int nchan, int softinv, int inv,
                                              b200fsk_rs41_frame_t *h_frames, int max_frames, int *nframes, int device, void *stream)
 {
-    if (!d_soft || !h_frames || !nframes || nchan <= 0 || (nbits < 0)) return B200FSK_EINVAL;
+    return b200fsk_rs41_frames_device(d_soft, stride, d_nbits, nbits, nchan, softinv, inv, 0, h_frames, max_frames, nframes, device, stream);
+}
+
+extern "C" int b200fsk_rs41_frames_device(const float *d_soft, long stride, const int *d_nbits, int nbits, int nchan, int softinv, int inv, int ecc,
+                                          b200fsk_rs41_frame_t *h_frames, int max_frames, int *nframes, int device, void *stream)
+{
+    if (!d_soft || !h_frames || !nframes || nchan <= 0 || (nbits < 0) || ecc < 0 || ecc > 2) return B200FSK_EINVAL;
     SCK(cudaSetDevice(device));
     static bool init = false;
     if (!init) {
@@ -139,19 +318,38 @@ extern "C" int b200fsk_rs41_framesync_device(const float *d_soft, long stride, c
     b200fsk_rs41_frame_t *d_fr = 0; int *d_cnt = 0;
     SCK(cudaMalloc(&d_fr, (size_t)nchan * maxpc * sizeof(b200fsk_rs41_frame_t))); SCK(cudaMalloc(&d_cnt, sizeof(int) * nchan));
     SsParams p; p.soft = d_soft; p.stride = stride; p.nbits_c = d_nbits; p.nbits = nbits; p.nchan = nchan; p.softinv = softinv ? 1 : 0; p.inv = inv ? 1 : 0;
-    p.maxpc = maxpc; p.frames = d_fr; p.counts = d_cnt;
+    p.maxpc = maxpc; p.ecc = ecc; p.frames = d_fr; p.counts = d_cnt;
     cudaStream_t s = (cudaStream_t)stream;
+    cudaEvent_t e0, e1; SCK(cudaEventCreate(&e0)); SCK(cudaEventCreate(&e1));
+    SCK(cudaEventRecord(e0, s));
     rs41_framesync_kernel<<<(nchan + SS_WARPS - 1) / SS_WARPS, SS_WARPS * 32, 0, s>>>(p);
+    SCK(cudaEventRecord(e1, s));
     SCK(cudaGetLastError());
     std::vector<int> cnt(nchan);
     SCK(cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(int) * nchan, cudaMemcpyDeviceToHost, s));
     SCK(cudaStreamSynchronize(s));
-    int tot = 0;
-    for (int c = 0; c < nchan; ++c) {
-        const int n = cnt[c] < maxpc ? cnt[c] : maxpc;
-        const int take = (tot + n <= max_frames) ? n : (max_frames - tot > 0 ? max_frames - tot : 0);
-        if (take > 0) SCK(cudaMemcpy(h_frames + tot, d_fr + (size_t)c * maxpc, (size_t)take * sizeof(b200fsk_rs41_frame_t), cudaMemcpyDeviceToHost));
-        tot += take;
+    SCK(cudaEventElapsedTime(&g_ss_ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    /* frame records: one copy of the used prefix of every channel's slot row when that is most of the buffer, else per channel */
+    int tot = 0, maxn = 0; long long sum = 0;
+    for (int c = 0; c < nchan; ++c) { const int n = cnt[c] < maxpc ? cnt[c] : maxpc; sum += n; if (n > maxn) maxn = n; }
+    if (sum > 0 && nchan > 8) {
+        std::vector<b200fsk_rs41_frame_t> all((size_t)nchan * maxn);
+        SCK(cudaMemcpy2D(all.data(), (size_t)maxn * sizeof(b200fsk_rs41_frame_t), d_fr, (size_t)maxpc * sizeof(b200fsk_rs41_frame_t),
+                         (size_t)maxn * sizeof(b200fsk_rs41_frame_t), nchan, cudaMemcpyDeviceToHost));
+        for (int c = 0; c < nchan; ++c) {
+            const int n = cnt[c] < maxpc ? cnt[c] : maxpc;
+            const int take = (tot + n <= max_frames) ? n : (max_frames - tot > 0 ? max_frames - tot : 0);
+            if (take > 0) memcpy(h_frames + tot, all.data() + (size_t)c * maxn, (size_t)take * sizeof(b200fsk_rs41_frame_t));
+            tot += take;
+        }
+    } else {
+        for (int c = 0; c < nchan; ++c) {
+            const int n = cnt[c] < maxpc ? cnt[c] : maxpc;
+            const int take = (tot + n <= max_frames) ? n : (max_frames - tot > 0 ? max_frames - tot : 0);
+            if (take > 0) SCK(cudaMemcpy(h_frames + tot, d_fr + (size_t)c * maxpc, (size_t)take * sizeof(b200fsk_rs41_frame_t), cudaMemcpyDeviceToHost));
+            tot += take;
+        }
     }
     *nframes = tot;
     cudaFree(d_fr); cudaFree(d_cnt);

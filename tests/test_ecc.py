@@ -1,0 +1,130 @@
+"""the Reed-Solomon stage of rs41mod (two interleaved RS(255,231) words per frame, retry with the fixed packet ids).
+CPU: oracle/ecc_oracle.c against the reference module itself (oracle/_ref/libbch_ref.so, word by word, also beyond t errors) and
+against `oracle/_ref/rs41mod -r [--ecc2] --softin -i` frame by frame.  GPU: the same stage inside the frame-sync kernel."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import rs41_frames as rf  # noqa: E402
+
+needs_bch = pytest.mark.skipif(not os.path.exists(os.path.join(po.REF_DIR, "libbch_ref.so")), reason="oracle/_ref/libbch_ref.so absent")
+needs_ref = pytest.mark.skipif(not os.path.exists(os.path.join(po.REF_DIR, "rs41mod")), reason="oracle/_ref/rs41mod absent")
+
+
+def test_crc16_known_answer(built):
+    # the reference hard-codes the CRC of the standard zero block 76 11 00..00 as EC C7 (rs41mod.c:1757-1758)
+    assert po.crc16(bytes(17)) == 0xC7EC
+    assert po.crc16(b"123456789") == 0x29B1                      # CRC-16/CCITT-FALSE check value
+
+
+def test_rs255_roundtrip(built):
+    rng = np.random.default_rng(1)
+    for nerr in (0, 1, 5, 11, 12):
+        msg = rng.integers(0, 256, 231, dtype=np.uint8)
+        cw = po.rs255_encode(msg)
+        assert po.rs255_decode(cw)[0] == 0
+        bad = cw.copy()
+        idx = rng.choice(255, nerr, replace=False)
+        bad[idx] ^= rng.integers(1, 256, nerr, dtype=np.uint8)
+        rc, fixed = po.rs255_decode(bad)
+        assert rc == nerr and np.array_equal(fixed, cw)
+
+
+@needs_bch
+def test_rs255_matches_reference_module(built):
+    """same return code and same output word as bch_ecc_mod.c's rs_decode for 0..30 symbol errors (miscorrections included)"""
+    enc, dec = po.ref_rs255()
+    rng = np.random.default_rng(2)
+    seen = set()
+    for trial in range(600):
+        msg = rng.integers(0, 256, 231, dtype=np.uint8)
+        cw = po.rs255_encode(msg)
+        assert np.array_equal(cw, enc(np.concatenate([np.zeros(24, np.uint8), msg])))
+        nerr = int(rng.integers(0, 31)) if trial % 3 else int(rng.integers(11, 16))
+        bad = cw.copy()
+        idx = rng.choice(255, nerr, replace=False)
+        bad[idx] ^= rng.integers(1, 256, nerr, dtype=np.uint8)
+        if trial % 50 == 7:
+            bad[:] = rng.integers(0, 256, 255, dtype=np.uint8)    # no codeword structure at all
+        r_rc, r_cw = dec(bad)
+        o_rc, o_cw = po.rs255_decode(bad)
+        assert o_rc == r_rc, (trial, nerr, o_rc, r_rc)
+        assert np.array_equal(o_cw, r_cw), (trial, nerr)
+        seen.add(r_rc if r_rc < 0 else 0)
+    assert {-1, 0} <= seen                                       # the failure exits were exercised (-2/-3 are rare)
+
+
+@needs_ref
+@pytest.mark.parametrize("ecc", [1, 2])
+@pytest.mark.parametrize("seed,sigma,burst", [(1, 0.30, None), (2, 0.40, None), (3, 0.45, None), (4, 0.50, None), (5, 0.38, (2, 0x39, 2)),
+                                               (6, 0.36, (1, 0x65, 30)), (7, 0.2, (3, 200, 40))])
+def test_rs41_ecc_oracle_matches_reference_rs41mod(built, ecc, seed, sigma, burst):
+    soft, clean = rf.soft_stream(seed, 8, sigma, burst=burst)
+    ref = po.ref_cli_rs41mod_raw(soft.tobytes(), inv=True, ecc=ecc)
+    mine = po.softsync_oracle(soft, False, True, ecc=ecc)
+    assert len(ref) == len(mine) >= 6
+    nok = 0
+    for m, (hexs, tag) in zip(mine, ref):
+        ec = m[5]
+        exp_tag = "[OK]" + (f" ({ec})" if ec > 0 else "") if ec >= 0 else "[NO] " + {-1: "(-+)", -2: "(+-)", -3: "(--)"}[ec]
+        assert tag.strip() == exp_tag, (tag, exp_tag)
+        assert m[3].tobytes().hex() == hexs
+        nok += ec >= 0
+    if sigma <= 0.30 and burst is None:
+        assert nok == len(mine) == len(clean)                    # and the corrected frames are the transmitted ones
+        for m, c in zip(mine, clean):
+            assert np.array_equal(m[3][:320], c)
+
+
+def test_crc_mask_and_clean_frames(built):
+    soft, clean = rf.soft_stream(11, 5, 0.25)
+    fr = po.softsync_oracle(soft, False, True, ecc=2)
+    assert len(fr) == 5
+    for m, c in zip(fr, clean):
+        assert m[5] >= 0 and m[6] == 0x3F and np.array_equal(m[3][:320], c)
+    soft, _ = rf.soft_stream(12, 5, 0.55)                          # hopeless: nothing decodes, and no block CRC survives
+    fr = po.softsync_oracle(soft, False, True, ecc=2)
+    assert all(m[5] < 0 for m in fr) and all(m[6] != 0x3F for m in fr)
+
+
+CASES = [(1, 0.30, None), (2, 0.40, None), (3, 0.45, None), (4, 0.50, None), (5, 0.38, (2, 0x39, 2)), (6, 0.36, (1, 0x65, 30)),
+         (7, 0.2, (3, 200, 40)), (8, 0.42, None), (9, 0.43, None), (10, 0.41, None)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ecc", [1, 2])
+def test_rs41_ecc_on_device(cuda, ecc):
+    """frame sync + Reed-Solomon + CRC in one kernel pass over soft bits in HBM: every frame identical (bytes, return code, CRC mask)
+    to the oracle, and to what the reference binary prints"""
+    import torch
+    from radiosonde_auto_rx_b200 import fsk
+    streams = [rf.soft_stream(s, 8, sg, burst=b)[0] for s, sg, b in CASES]
+    streams[3] = streams[3][: streams[3].size - 3000]              # one stream ends inside a frame (EOF rule, rs41mod.c:2481-2484)
+    n = max(s.size for s in streams)
+    buf = np.zeros((len(streams), n), np.float32)
+    for i, s in enumerate(streams):
+        buf[i, : s.size] = s
+    d = torch.from_numpy(buf).cuda()
+    nb = torch.tensor([s.size for s in streams], dtype=torch.int32, device="cuda")
+    got = fsk.rs41_framesync_device(d, n, nb, len(streams), softinv=False, inv=True, ecc=ecc)
+    total = rescued = 0
+    for c, s in enumerate(streams):
+        exp = po.softsync_oracle(s, False, True, ecc=ecc)
+        mine = [g for g in got if g[0] == c]
+        assert len(mine) == len(exp)
+        for g, e in zip(mine, exp):
+            assert (g[1], g[2], g[5], g[6], g[7]) == (e[0], e[1], e[4], e[5], e[6]), (c, g[:3], g[5:], e[:2], e[4:])
+            assert g[4].tobytes() == e[3].tobytes(), (c, g[2])
+        if os.path.exists(os.path.join(po.REF_DIR, "rs41mod")):
+            ref = po.ref_cli_rs41mod_raw(s.tobytes(), inv=True, ecc=ecc)
+            assert len(ref) == len(mine)
+            for (hexs, tag), g in zip(ref, mine):
+                assert g[4].tobytes().hex() == hexs and tag.strip().startswith("[OK]" if g[6] >= 0 else "[NO]")
+        total += len(mine)
+        rescued += sum(1 for g in mine if g[6] > 0)
+    assert total >= 70 and rescued >= 20
