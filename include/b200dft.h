@@ -94,6 +94,24 @@ int  b200dft_channelise_device(b200dft_t *h, const void *d_wide, int fmt, long n
                                long *nout);
 int  b200dft_last_channelise_ms(b200dft_t *h, float *ms);
 
+/* ---- scanner peak stage: where to point the detector -------------------------------------------------------------
+ * auto_rx: rtl_power spectrum -> median noise floor -> detect_peaks -> sorted / quantised / clipped candidate list
+ * (auto_rx/autorx/scan.py:974-1063, auto_rx/autorx/utils.py:435-586).  Here the spectrum is computed from the capture that is
+ * already in HBM for the channeliser, so candidates and detections come from the same samples. */
+/* averaged Hann periodogram: power_db[k] / freq_hz[k], k < nfft (power of two, 64..16384), ascending frequency around centre_hz;
+ * *step_hz = sr_base/nfft.  (rtl_power is an external program: no reference restatement exists for this function.) */
+int  b200dft_scan_psd_device(const void *d_wide, int fmt, long nwide, int sr_base, double centre_hz, int nfft, double *freq_hz,
+                             double *power_db, double *step_hz, int device, float *kernel_ms);
+/* detect_peaks(x, mph, mpd) with the other arguments at the values sonde_search uses (utils.py:435-586); returns the peak count,
+ * indices ascending in idx_out (at most max_out written).  use_mph = 0: mph=None. */
+int  b200dft_scan_detect_peaks(const double *x, int n, int use_mph, double mph, double mpd, int *idx_out, int max_out);
+/* scan.py:1005-1063: noise floor (median), peaks above floor + snr_threshold at least min_distance apart, strongest first, rounded to
+ * quantization, duplicates dropped, outside [min_freq, max_freq] +- quantization/2 dropped, first max_peaks kept. */
+int  b200dft_scan_candidates(const double *freq_hz, const double *power_db, int n, double step_hz, double snr_threshold_db, double min_distance_hz,
+                             double quantization_hz, double min_freq_hz, double max_freq_hz, int max_peaks, double *out_hz, int max_out,
+                             double *noise_floor_db);
+const char *b200dft_scan_last_error(void);
+
 long  b200dft_launch_count(const b200dft_t *h);
 /* device time (ms) of the front-end kernels and of the correlator kernel in the most recent run */
 int   b200dft_last_kernel_ms(b200dft_t *h, float *front_ms, float *corr_ms);

@@ -426,3 +426,70 @@ def ref_rs255():
         ep, ev = (C.c_ubyte * 32)(), (C.c_ubyte * 32)()
         return L.rs_decode(rs, c.ctypes.data_as(C.c_void_p), ep, ev), c
     return enc, dec
+
+
+# ------------------------------------------------------------------------------------------------
+# scanner peak stage: numpy restatements -- test infrastructure only
+# ------------------------------------------------------------------------------------------------
+def detect_peaks_oracle(x, mph=None, mpd=1):
+    """autorx.utils.detect_peaks (utils.py:435-586) with edge='rising', threshold=0, kpsh=False, valley=False; pinned by
+    tests/golden/golden_peaks.json (outputs of the reference function itself)."""
+    x = np.atleast_1d(x).astype("float64").copy()
+    if x.size < 3:
+        return np.array([], dtype=int)
+    dx = x[1:] - x[:-1]
+    nan = np.isnan(x)
+    if nan.any():
+        x[nan] = np.inf
+        dx[np.isnan(dx)] = np.inf
+    nxt, prv = np.append(dx, 0.0), np.insert(dx, 0, 0.0)
+    ind = np.where((nxt <= 0) & (prv > 0))[0]                                   # :537-539
+    if ind.size and nan.any():
+        bad = nan.copy(); bad[:-1] |= nan[1:]; bad[1:] |= nan[:-1]              # :543-550
+        ind = ind[~bad[ind]]
+    if ind.size and ind[0] == 0:
+        ind = ind[1:]
+    if ind.size and ind[-1] == x.size - 1:
+        ind = ind[:-1]
+    if ind.size and mph is not None:
+        ind = ind[x[ind] >= mph]
+    if ind.size and mpd > 1:                                                     # :564-576
+        order = ind[np.argsort(x[ind], kind="stable")][::-1]
+        dele = np.zeros(order.size, bool)
+        for i in range(order.size):
+            if not dele[i]:
+                dele |= (order >= order[i] - mpd) & (order <= order[i] + mpd)
+                dele[i] = False
+        ind = np.sort(order[~dele])
+    return ind
+
+
+def scan_candidates_oracle(freq, power, step, snr_threshold=10.0, min_distance=1000.0, quantization=10000.0, min_freq_hz=-np.inf,
+                           max_freq_hz=np.inf, max_peaks=10):
+    """The candidate list built inside SondeScanner.sonde_search (scan.py:1005-1063), frequencies in Hz."""
+    freq, power = np.asarray(freq, float), np.asarray(power, float)
+    nf = np.median(power)
+    pk = detect_peaks_oracle(power, mph=nf + snr_threshold, mpd=min_distance / step)
+    if pk.size == 0:
+        return np.array([]), nf
+    pf = freq[pk][np.argsort(power[pk], kind="stable")][::-1]
+    pf = np.round(pf / quantization) * quantization
+    _, first = np.unique(pf, return_index=True)
+    pf = pf[np.sort(first)]
+    pf = pf[~((pf < min_freq_hz - quantization / 2.0) | (pf > max_freq_hz + quantization / 2.0))]
+    return pf[:max_peaks], nf
+
+
+def psd_oracle(iq: np.ndarray, nfft: int):
+    """float64 averaged periodic-Hann periodogram, fftshifted, dB: what b200dft_scan_psd_device computes (no reference: rtl_power is external)."""
+    if iq.dtype == np.int16:
+        z = (iq[:, 0].astype(np.float64) + 1j * iq[:, 1]) / 32768.0
+    elif iq.dtype == np.uint8:
+        z = ((iq[:, 0].astype(np.float64) - 128) + 1j * (iq[:, 1].astype(np.float64) - 128)) / 128.0
+    else:
+        z = iq[:, 0].astype(np.float64) + 1j * iq[:, 1]
+    nseg = z.size // nfft
+    w = (0.5 - 0.5 * np.cos(2 * np.pi * np.arange(nfft) / nfft)).astype(np.float32).astype(np.float64)
+    S = np.abs(np.fft.fft(z[: nseg * nfft].reshape(nseg, nfft) * w, axis=1)) ** 2
+    p = S.mean(axis=0) / (w ** 2).sum()
+    return 10.0 * np.log10(np.fft.fftshift(p))

@@ -209,3 +209,51 @@ class DftWidebandBatch(DftDetectBatch):
         ms = C.c_float(0)
         _ck(self.L.b200dft_last_channelise_ms(self.h, C.byref(ms)))
         return ms.value
+
+
+# ---- scanner peak stage ------------------------------------------------------------------------------------
+def scan_psd(d_wide, fmt: str, nwide: int, sr_base: int, centre_hz: float = 0.0, nfft: int = 8192, device: int = 0):
+    """(freq_hz, power_db, step_hz, kernel_ms): the triple auto_rx reads from rtl_power (sdr_wrappers.get_power_spectrum), computed on
+    the GPU from the capture the channeliser uses."""
+    L = lib()
+    L.b200dft_scan_psd_device.argtypes = [C.c_void_p, C.c_int, C.c_long, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p,
+                                          C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_float)]
+    L.b200dft_scan_last_error.restype = C.c_char_p
+    f, p = np.zeros(nfft), np.zeros(nfft)
+    step, ms = C.c_double(0), C.c_float(0)
+    ptr = d_wide.data_ptr() if hasattr(d_wide, "data_ptr") else int(d_wide)
+    rc = L.b200dft_scan_psd_device(C.c_void_p(ptr), {"cs16": 0, "f32": 1, "cu8": 2}[fmt], nwide, sr_base, float(centre_hz), nfft,
+                                   f.ctypes.data, p.ctypes.data, C.byref(step), device, C.byref(ms))
+    if rc:
+        raise B200DftError(f"scan_psd error {rc}: {L.b200dft_scan_last_error().decode()}")
+    return f, p, step.value, ms.value
+
+
+def detect_peaks(x, mph=None, mpd=1):
+    """autorx.utils.detect_peaks(x, mph, mpd) (utils.py:435) -> ascending peak indices."""
+    L = lib()
+    L.b200dft_scan_detect_peaks.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_int]
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    idx = np.zeros(max(x.size, 1), np.int32)
+    n = L.b200dft_scan_detect_peaks(x.ctypes.data, x.size, int(mph is not None), float(mph or 0.0), float(mpd), idx.ctypes.data, idx.size)
+    if n < 0:
+        raise B200DftError(f"detect_peaks error {n}")
+    return idx[:n].astype(np.int64)
+
+
+def scan_candidates(freq_hz, power_db, step_hz, snr_threshold=10.0, min_distance=1000.0, quantization=10000.0, min_freq_hz=-np.inf,
+                    max_freq_hz=np.inf, max_peaks=10):
+    """The candidate list of SondeScanner.sonde_search (scan.py:1005-1063) -> (frequencies in Hz strongest first, noise floor dB)."""
+    L = lib()
+    L.b200dft_scan_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_double] * 6 + [C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+    f = np.ascontiguousarray(freq_hz, dtype=np.float64)
+    p = np.ascontiguousarray(power_db, dtype=np.float64)
+    out = np.zeros(max(f.size, 1))
+    nf = C.c_double(0)
+    lo = -1e300 if not np.isfinite(min_freq_hz) else float(min_freq_hz)
+    hi = 1e300 if not np.isfinite(max_freq_hz) else float(max_freq_hz)
+    n = L.b200dft_scan_candidates(f.ctypes.data, p.ctypes.data, f.size, float(step_hz), float(snr_threshold), float(min_distance), float(quantization),
+                                  lo, hi, int(max_peaks), out.ctypes.data, out.size, C.byref(nf))
+    if n < 0:
+        raise B200DftError(f"scan_candidates error {n}")
+    return out[:n].copy(), nf.value
