@@ -259,7 +259,7 @@ __device__ __forceinline__ void estimate_tones(const FskKParams &p, const float 
 __global__ void __launch_bounds__(FSK_THREADS) fsk_demod_kernel(const FskKParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ float2 s_phi[4], s_dphi[4];
+    __shared__ float2 s_phi[4];
     __shared__ int    s_tabidx[4];
     __shared__ float  s_tc[2];
     __shared__ int    s_nin, s_low, s_high, s_nan;

@@ -482,7 +482,6 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
         const int numffts = (int)floorf(__fdiv_rn((float)nin_min, (float)(Ndft / 2))) - 1;   /* same for all 3 nin (host-checked) */
         float2 *F = fftbuf + ew * PIPE_NFB * (Ndft + (Ndft >> 3));       /* PIPE_NFB padded buffers: i -> i + i/8 */
         unsigned par_pub = 0;
-        const int npl = (Ndft + 31) >> 5;                                /* samples per lane per window (<= 8: Ndft <= 256) */
         PDECL
         for (int k = 0;; ++k) {
             { PTIC

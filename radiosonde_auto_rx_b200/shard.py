@@ -4,7 +4,9 @@ The hot path partitions by channel: GPU g owns a contiguous block of narrowband 
 demodulator state for ever; no data-path collective exists.  A collective is used only to DISTRIBUTE input when one
 rank holds a shared capture: ``scatter_capture`` (torch.distributed.scatter -- NCCL over NVLink on GPUs, gloo on CPU
 for the tests) hands every rank its [channels_g, nsamp, 2] slab; results (bits, detections) stay per rank and only
-tiny per-channel counters are gathered.
+tiny per-channel counters are gathered.  For a WIDEBAND capture (BASELINE cfg5) every rank needs the whole
+buffer and owns a block of candidate frequencies instead: ``broadcast_capture`` (one NCCL broadcast, 4 B per wide sample)
+followed by ``shard_range`` over the candidate list.
 """
 from __future__ import annotations
 
@@ -40,6 +42,20 @@ def scatter_capture(iq_root, nchan_total: int, nsamp: int, src: int = 0, device=
             chunks.append(t.view(torch.uint8).reshape(per, nsamp * 4))
     dist.scatter(recv, chunks, src=src)
     return recv.view(torch.int16).reshape(per, nsamp, 2)[: hi - lo]
+
+
+def broadcast_capture(wide_root, nwide: int, src: int = 0, device=None):
+    """Rank `src` passes one wideband capture (int16 [nwide, 2]); every rank returns it as a torch tensor on `device`.
+    (torch.distributed.broadcast: NCCL over NVLink / NVSwitch on GPUs -- 38 MB per second of 9.6 MHz capture, gloo in the CPU test.)"""
+    import torch
+    import torch.distributed as dist
+    dev = device if device is not None else "cpu"
+    buf = torch.empty(nwide * 4, dtype=torch.uint8, device=dev)              # raw bytes: gloo has no int16
+    if dist.get_rank() == src:
+        full = torch.as_tensor(np.ascontiguousarray(wide_root) if isinstance(wide_root, np.ndarray) else wide_root)
+        buf.copy_(full.reshape(-1).view(torch.uint8))
+    dist.broadcast(buf, src=src)
+    return buf.view(torch.int16).reshape(nwide, 2)
 
 
 def gather_counts(local_counts, nchan_total: int, dst: int = 0, device=None):

@@ -61,3 +61,44 @@ def test_scatter_shard_gather_world2(built):
         out, _, recs = po.Oracle(po.RS41).run_stream(iq[c])
         assert f_all[c] == len(recs)
         assert s_all[c] == int(np.frombuffer(out.tobytes(), dtype=np.uint32).astype(np.uint64).sum() % (1 << 62))
+
+
+def _wb_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from oracle import pyoracle as po
+    from radiosonde_auto_rx_b200 import siggen
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sr, hz = 1000000, [200e3, -300e3, 50e3]
+    n = int(sr * 1.3)
+    wide = siggen.wideband_mix(12, n, sr, [("RS41", 200e3), ("LMS6", -300e3)], snr_db=8.0) if rank == 0 else None
+    mine = shard.broadcast_capture(wide, n, src=0).numpy()
+    lo, hi = shard.shard_range(len(hz), world, rank)                 # each rank owns a block of candidate frequencies
+    codes = [po.dft_oracle_run_wideband(mine, sr, hz[c] / sr, 15.0, True, False)[0] for c in range(lo, hi)]   # the oracle stands in for the GPU
+    allc = shard.gather_counts(codes, len(hz))
+    if rank == 0:
+        q.put((allc.tolist(), int(np.abs(mine.astype(np.int64)).sum())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_broadcast_capture_shard_candidates_world2(built):
+    """wideband mode: one capture to every rank, candidates sharded, exit codes gathered == single-process run"""
+    import torch.multiprocessing as mp
+    from oracle import pyoracle as po
+    from radiosonde_auto_rx_b200 import siggen
+    world = 2
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_wb_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in ps]
+    codes, chk = q.get(timeout=180)
+    [p.join(60) for p in ps]
+    assert all(p.exitcode == 0 for p in ps)
+    sr = 1000000
+    wide = siggen.wideband_mix(12, int(sr * 1.3), sr, [("RS41", 200e3), ("LMS6", -300e3)], snr_db=8.0)
+    assert chk == int(np.abs(wide.astype(np.int64)).sum())
+    exp = [po.dft_oracle_run_wideband(wide, sr, f / sr, 15.0, True, False)[0] for f in (200e3, -300e3, 50e3)]
+    assert codes == exp and exp[0] == 3 and exp[1] == 8 and exp[2] == 0
