@@ -13,6 +13,33 @@ __device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigne
 __device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) { unsigned long long d; asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 __device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) { unsigned long long d; asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 
+__device__ __forceinline__ void sts128(float2 *dst, float2 a, float2 b)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
+}
+// the software-pipelined loop of fsk_pipe_kernel.cuh::osc_pairs (two register sets, stores of one set between the steps of the other)
+__device__ __forceinline__ float2 osc_pipelined(float2 ph, const float2 d, float2 *dst, int n)
+{
+    int j = 0;
+    float2 a[8], b[8];
+    a[0] = cmul_rn(ph, d);
+#pragma unroll
+    for (int s = 1; s < 8; ++s) a[s] = cmul_rn(a[s - 1], d);
+    for (; j + 32 <= n; j += 16) {
+        b[0] = cmul_rn(a[7], d);
+#pragma unroll
+        for (int s = 1; s < 8; ++s) { b[s] = cmul_rn(b[s - 1], d); if (s & 1) sts128(dst + j + s - 1, a[s - 1], a[s]); }
+        a[0] = cmul_rn(b[7], d);
+#pragma unroll
+        for (int s = 1; s < 8; ++s) { a[s] = cmul_rn(a[s - 1], d); if (s & 1) sts128(dst + j + 8 + s - 1, b[s - 1], b[s]); }
+    }
+#pragma unroll
+    for (int s = 1; s < 8; s += 2) sts128(dst + j + s - 1, a[s - 1], a[s]);
+    ph = a[7]; j += 8;
+    for (; j < n; j += 2) { float2 x = cmul_rn(ph, d); ph = cmul_rn(x, d); *(float4 *)(dst + j) = make_float4(x.x, x.y, ph.x, ph.y); }
+    return ph;
+}
+
 template <int MODE> __global__ void k(float2 *out, const float2 *dtab, long long *cyc, int nactive_warps)
 {
     extern __shared__ float2 ring[];
@@ -54,6 +81,8 @@ template <int MODE> __global__ void k(float2 *out, const float2 *dtab, long long
                                      __fadd_rn(__uint_as_float((unsigned)(t >> 32)), __uint_as_float((unsigned)(u >> 32))));
                     *(float4 *)(dst + j) = make_float4(a.x, a.y, ph.x, ph.y);
                 }
+            } else if (MODE == 5) {    // software-pipelined, STS.128 of the previous 8 steps between the current ones
+                ph = osc_pipelined(ph, d, dst, STEPS - (STEPS & 1));
             } else if (MODE == 3) {    // scalar without any store (pure chain)
 #pragma unroll 8
                 for (int j = 0; j < STEPS; ++j) { ph = cmul_rn(ph, d); }
@@ -94,5 +123,7 @@ int main()
     run<3>("scalar, no store (pure chain)", 1, out, dtab, cyc);
     run<4>("FMUL2 products + scalar FADD, STS.128/2", 1, out, dtab, cyc);
     run<4>("FMUL2 products + scalar FADD, STS.128/2", 5, out, dtab, cyc);
+    for (int w : {1, 2, 5, 8}) run<5>("software-pipelined 2x8 steps, STS.128 interleaved", w, out, dtab, cyc);
+    for (int w : {2, 5, 8}) run<1>("scalar, STS.128 per 2 steps", w, out, dtab, cyc);
     return 0;
 }

@@ -121,11 +121,48 @@ __device__ __forceinline__ bool warp_wait_ge(const int *flag, int want, const in
 }
 __device__ __forceinline__ void group_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-/* n oscillator steps (n even, dst 16-byte aligned) written to consecutive ring slots; paired 16-byte stores. */
+/* 16-byte shared store that the scheduler must keep where it is written (see osc_pairs) */
+__device__ __forceinline__ void sts128(float2 *dst, float2 a, float2 b)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
+}
+
+/* n oscillator steps (n even, dst 16-byte aligned) written to consecutive ring slots; paired 16-byte stores.
+ * The recurrence is one dependent FMUL->FADD chain per lane; what it must not do is wait for its own stores.  A shared store reads its
+ * source registers only when the memory pipe dequeues it, and until then the next write to those registers stalls (write-after-read on
+ * the short scoreboard: 18 % of this warp's samples in the round-1 profile, more when a second CTA loads the same SM's memory pipe).
+ * With PIPE_OSC_PIPELINED the loop is software-pipelined over two register sets of 8 steps: while set B is being computed the pairs of
+ * set A are stored one by one between the steps, and vice versa -- every stored register is rewritten 8 steps (~100 cycles) after its
+ * store was issued.  Measured (profiles/r01_notes.md): 17.8 -> 15.1 cycles/step with one channel per SM, but no gain (22-24 -> 26) with
+ * two channels per SM, where the stores queue behind the other warps' shared-memory traffic wherever they are placed; the headline
+ * configuration (256 channels on 148 SMs) is in the second regime, so the default stays the plain loop. */
+#ifndef PIPE_OSC_PIPELINED
+#define PIPE_OSC_PIPELINED 0
+#endif
 __device__ __forceinline__ float2 osc_pairs(float2 ph, const float2 d, float2 *dst, int n)
 {
+    int j = 0;
+#if PIPE_OSC_PIPELINED
+    if (n >= 32) {
+        float2 a[8], b[8];
+        a[0] = cmul_rn(ph, d);
+#pragma unroll
+        for (int s = 1; s < 8; ++s) a[s] = cmul_rn(a[s - 1], d);
+        for (; j + 32 <= n; j += 16) {                       /* invariant: a[] = steps j+1..j+8, not stored yet */
+            b[0] = cmul_rn(a[7], d);
+#pragma unroll
+            for (int s = 1; s < 8; ++s) { b[s] = cmul_rn(b[s - 1], d); if (s & 1) sts128(dst + j + s - 1, a[s - 1], a[s]); }
+            a[0] = cmul_rn(b[7], d);
+#pragma unroll
+            for (int s = 1; s < 8; ++s) { a[s] = cmul_rn(a[s - 1], d); if (s & 1) sts128(dst + j + 8 + s - 1, b[s - 1], b[s]); }
+        }
+#pragma unroll
+        for (int s = 1; s < 8; s += 2) sts128(dst + j + s - 1, a[s - 1], a[s]);
+        ph = a[7]; j += 8;
+    }
+#endif
 #pragma unroll 4
-    for (int j = 0; j < n; j += 2) {
+    for (; j < n; j += 2) {
         const float2 a = cmul_rn(ph, d);
         ph = cmul_rn(a, d);
         *reinterpret_cast<float4 *>(dst + j) = make_float4(a.x, a.y, ph.x, ph.y);
