@@ -871,8 +871,9 @@ extern "C" int b200dft_create_wideband(b200dft_t **out, int sr_base, double bw_k
     h->wmaxcnt = IF_sr / 32; if (decM > 1) h->wmaxcnt *= decM;                     /* :1155-1156 */
     int maxsmem = 0;
     CK(cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-    int tm = 64;                                                                   /* outputs per CTA: window <= ~96 KB */
-    while (tm > 1 && ((size_t)tm * decM + taps) * sizeof(float2) > 100 * 1024) tm >>= 1;
+    int tm = 64, budget_kb = 100;                                                  /* outputs per CTA: window <= budget (occupancy vs. re-rotated overlap) */
+    if (const char *e = getenv("B200DFT_CH_SMEM_KB")) { const int v = atoi(e); if (v >= 16 && v <= 200) budget_kb = v; }   /* tuning knob for profiles/wideband_bench.py */
+    while (tm > 1 && ((size_t)tm * decM + taps) * sizeof(float2) > (size_t)budget_kb * 1024) tm >>= 1;
     h->ch_tm = tm; h->ch_smem = ((size_t)tm * decM + taps) * sizeof(float2) + (size_t)taps * sizeof(float) + 16;
     if (h->ch_smem + 1024 > (size_t)maxsmem) { b200dft_destroy(h); *out = 0; return fail(B200DFT_EINVAL, "decimation filter does not fit shared memory"); }
     {   cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, (const void *)dft_chan_kernel));
