@@ -4,7 +4,7 @@
 
     python tests/golden/make_golden.py
 
-Outputs (committed): golden_fsk.npz, golden_dft.json, golden_dft_wb.json.  The inputs are regenerated from seeds by
+Outputs (committed): golden_fsk.npz, golden_dft.json, golden_dft_wb.json, golden_rs41.json.  The inputs are regenerated from seeds by
 radiosonde_auto_rx_b200.siggen, so only outputs + an input checksum are stored.
 """
 import hashlib
@@ -54,6 +54,11 @@ DFT_WB_CASES = {
 }
 
 
+# soft-bit streams of tests/rs41_frames.py: (seed, noise sigma, burst) -- the cases of tests/test_ecc.py
+RS41_CASES = [(1, 0.30, None), (2, 0.40, None), (3, 0.45, None), (4, 0.50, None), (5, 0.38, (2, 0x39, 2)), (6, 0.36, (1, 0x65, 30)),
+              (7, 0.2, (3, 200, 40)), (8, 0.42, None), (9, 0.43, None), (10, 0.41, None)]
+
+
 def dft_wb_input(name):
     sr, secs, seed, emit, _ = DFT_WB_CASES[name]
     return siggen.wideband_mix(seed, int(sr * secs), sr, emit, snr_db=6.0, dc=(250.0, -150.0))
@@ -89,7 +94,19 @@ def main():
             rc, dets = po.ref_cli_dft_detect(iq, sr, 15.0, True, True, fq=f / sr)     # dft_detect -v -c --IQ fq --bw 15 --dc - sr 16
             wj[name]["fq"][repr(f)] = {"exit_code": rc, "dets": dets}
     json.dump(wj, open(os.path.join(HERE, "golden_dft_wb.json"), "w"), indent=1)
-    print("wrote golden_fsk.npz, golden_dft.json, golden_dft_wb.json")
+    # RS41 frame sync + Reed-Solomon stage: what `rs41mod -r [--ecc2] --softin -i` prints for seeded soft-bit streams
+    sys.path.insert(0, os.path.dirname(HERE))
+    import rs41_frames as rf
+    rj = {}
+    for seed, sigma, burst in RS41_CASES:
+        soft, _ = rf.soft_stream(seed, 8, sigma, burst=burst)
+        ent = {"sha": hashlib.sha256(soft.tobytes()).hexdigest()}
+        for ecc in (1, 2):
+            ref = po.ref_cli_rs41mod_raw(soft.tobytes(), inv=True, ecc=ecc)
+            ent[f"ecc{ecc}"] = [[hashlib.sha1(h.encode()).hexdigest()[:16], t.strip()] for h, t in ref]
+        rj[str(seed)] = ent
+    json.dump(rj, open(os.path.join(HERE, "golden_rs41.json"), "w"), indent=1)
+    print("wrote golden_fsk.npz, golden_dft.json, golden_dft_wb.json, golden_rs41.json")
 
 
 if __name__ == "__main__":

@@ -92,8 +92,49 @@ def test_crc_mask_and_clean_frames(built):
     assert all(m[5] < 0 for m in fr) and all(m[6] != 0x3F for m in fr)
 
 
-CASES = [(1, 0.30, None), (2, 0.40, None), (3, 0.45, None), (4, 0.50, None), (5, 0.38, (2, 0x39, 2)), (6, 0.36, (1, 0x65, 30)),
-         (7, 0.2, (3, 200, 40)), (8, 0.42, None), (9, 0.43, None), (10, 0.41, None)]
+import hashlib  # noqa: E402
+import importlib.util  # noqa: E402
+import json  # noqa: E402
+
+_spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_golden.py"))
+_mg = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(_mg)
+CASES = _mg.RS41_CASES
+GR = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_rs41.json")))
+
+
+def _tag(ec):
+    return ("[OK]" + (f" ({ec})" if ec > 0 else "")) if ec >= 0 else "[NO] " + {-1: "(-+)", -2: "(+-)", -3: "(--)"}[ec]
+
+
+@pytest.mark.parametrize("ecc", [1, 2])
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"seed{c[0]}")
+def test_rs41_oracle_reproduces_golden(built, case, ecc):
+    """recorded output of the reference binary (tests/golden/golden_rs41.json): works without oracle/_ref"""
+    seed, sigma, burst = case
+    soft, _ = rf.soft_stream(seed, 8, sigma, burst=burst)
+    g = GR[str(seed)]
+    assert hashlib.sha256(soft.tobytes()).hexdigest() == g["sha"]
+    mine = po.softsync_oracle(soft, False, True, ecc=ecc)
+    assert [[hashlib.sha1(m[3].tobytes().hex().encode()).hexdigest()[:16], _tag(m[5])] for m in mine] == g[f"ecc{ecc}"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ecc", [1, 2])
+def test_rs41_cuda_reproduces_golden(cuda, ecc):
+    """the kernel straight against the reference's recorded frames (no oracle in between)"""
+    import torch
+    from radiosonde_auto_rx_b200 import fsk
+    streams = [rf.soft_stream(s, 8, sg, burst=b)[0] for s, sg, b in CASES]
+    n = max(s.size for s in streams)
+    buf = np.zeros((len(streams), n), np.float32)
+    for i, s in enumerate(streams):
+        buf[i, : s.size] = s
+    nb = torch.tensor([s.size for s in streams], dtype=torch.int32, device="cuda")
+    got = fsk.rs41_framesync_device(torch.from_numpy(buf).cuda(), n, nb, len(streams), ecc=ecc)
+    for c, (seed, _, _) in enumerate(CASES):
+        mine = [[hashlib.sha1(g[4].tobytes().hex().encode()).hexdigest()[:16], _tag(g[6])] for g in got if g[0] == c]
+        assert mine == GR[str(seed)][f"ecc{ecc}"], (seed, ecc)
 
 
 @pytest.mark.gpu
