@@ -153,6 +153,15 @@ int  b200fsk_rs41_framesync_device(const float *d_soft, long stride, const int *
  * (auto_rx/autorx/decode.py:909).  bytes[] then holds the corrected frame, exactly what `rs41mod -r` prints. */
 int  b200fsk_rs41_frames_device(const float *d_soft, long stride, const int *d_nbits, int nbits, int nchan, int softinv, int inv, int ecc,
                                 b200fsk_rs41_frame_t *h_frames, int max_frames, int *nframes, int device, void *stream);
+/* Streaming form: one handle = nchan running streams (what one `rs41mod --softin` process per channel keeps between reads: header
+ * ring, frame buffer, position inside a frame).  Each push continues where the previous one stopped, a frame that straddles two pushes
+ * is returned by the push that completes it; flush != 0 marks end of stream (a frame cut short is then returned the way the reference
+ * prints it at EOF, rs41mod.c:2481-2484).  The whole-buffer calls above are create + push(flush) + destroy. */
+typedef struct b200fsk_rs41sync b200fsk_rs41sync_t;
+int  b200fsk_rs41sync_create(b200fsk_rs41sync_t **out, int nchan, int softinv, int inv, int ecc, int device);
+int  b200fsk_rs41sync_push_device(b200fsk_rs41sync_t *h, const float *d_soft, long stride, const int *d_nbits, int nbits, int flush,
+                                  b200fsk_rs41_frame_t *h_frames, int max_frames, int *nframes, void *stream);
+void b200fsk_rs41sync_destroy(b200fsk_rs41sync_t *h);
 const char *b200fsk_framesync_last_error(void);
 /* device time (ms, CUDA events) of the frame-sync kernel in this thread's most recent call; < 0 if none */
 float b200fsk_framesync_last_kernel_ms(void);

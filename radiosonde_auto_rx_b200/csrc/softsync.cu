@@ -39,8 +39,8 @@ static const unsigned char RS41_MASK[64] = {
     0xD0, 0xBC, 0xB4, 0xB6, 0x06, 0xAA, 0xF4, 0x23, 0x78, 0x6E, 0x3B, 0xAE, 0xBF, 0x7B, 0x4C, 0xC1};
 
 struct SsParams {
-    const float *soft; long long stride; const int *nbits_c; int nbits; int nchan, softinv, inv, maxpc, ecc;
-    b200fsk_rs41_frame_t *frames; int *counts;
+    const float *soft; long long stride; const int *nbits_c; int nbits; int nchan, softinv, inv, maxpc, ecc, flush;
+    b200fsk_rs41_frame_t *frames; int *counts; struct SsState *state;
 };
 
 /* ---- GF(2^8) f = 0x11D, alpha = 2 (bch_ecc_mod.c:55-59): exp table doubled so products need no modulo -------------------- */
@@ -188,11 +188,25 @@ __device__ unsigned rs41_crc_mask_warp(const unsigned char *frame, int lane)
     return __ballot_sync(0xffffffffu, ok) & 0x3Fu;
 }
 
+/* Per-channel state that survives between pushes of one stream (all of it is what the reference keeps in its process: the header ring
+ * hdb.sbuf, gpx->frame / frm_bytescore, the position inside a frame, plus the <8 soft bits of an unfinished byte). */
+struct SsState {
+    int mode;                      /* 0: searching for a header, 1: inside a frame */
+    int byte_count, ncarry, nframes_total;
+    long long consumed;            /* soft bits handed in by earlier pushes */
+    long long first_bit; float mv; /* of the frame in progress */
+    float ring[64];                /* last 63 scanned bits (search) / the ring as the hit left it (in frame) */
+    float carry[8];                /* bits of an incomplete byte, logically in front of the next push */
+    unsigned char frame[SS_FRAME_LEN + 2];
+    float score[SS_FRAME_LEN];
+};
+
 __global__ void __launch_bounds__(SS_WARPS * 32) rs41_framesync_kernel(const SsParams p)
 {
     __shared__ float s_w[SS_WARPS][96];
     __shared__ unsigned char s_frame[SS_WARPS][SS_FRAME_LEN + 2];
     __shared__ float s_score[SS_WARPS][SS_FRAME_LEN];
+    __shared__ float s_carry[SS_WARPS][8];
     __shared__ GfTab s_gf;
     __shared__ unsigned char s_cw[SS_WARPS][2][256];
     __shared__ RsScratch s_rs[SS_WARPS];
@@ -206,49 +220,59 @@ __global__ void __launch_bounds__(SS_WARPS * 32) rs41_framesync_kernel(const SsP
     }
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5, c = blockIdx.x * SS_WARPS + wp;
     if (c >= p.nchan) return;
-    float *w = s_w[wp]; unsigned char *frame = s_frame[wp]; float *score = s_score[wp];
+    float *w = s_w[wp]; unsigned char *frame = s_frame[wp]; float *score = s_score[wp]; float *carry = s_carry[wp];
+    SsState &st = p.state[c];
     const float *soft = p.soft + (long long)c * p.stride;
-    const int nbits = p.nbits_c ? p.nbits_c[c] : p.nbits;
-    for (int i = lane; i < 96; i += 32) w[i] = 0.0f;                          /* hdb.sbuf = calloc (rs41mod.c:2865) */
-    for (int i = lane; i < SS_FRAME_LEN; i += 32) { frame[i] = 0; score[i] = 0.0f; }
+    /* this push = the carried bits of an unfinished byte followed by the new soft bits */
+    const int ncarry = st.ncarry;
+    const int nb = ncarry + (p.nbits_c ? p.nbits_c[c] : p.nbits);
+    const long long base = st.consumed - ncarry;                              /* stream index of local bit 0 */
+    for (int i = lane; i < 96; i += 32) w[i] = i < 63 ? st.ring[i] : 0.0f;   /* first push: zeros = calloc'ed hdb.sbuf (rs41mod.c:2865) */
+    for (int i = lane; i < SS_FRAME_LEN; i += 32) { frame[i] = st.frame[i]; score[i] = st.score[i]; }
+    if (lane < 8) carry[lane] = st.carry[lane];
     __syncwarp();
-    if (lane < 8) { const unsigned char hb[8] = {0x86, 0x35, 0xf4, 0x40, 0x93, 0xdf, 0x1a, 0x60}; frame[lane] = hb[lane]; }   /* rs41mod.c:2766 */
-    __syncwarp();
-    int pos = 0, nf = 0;
-    while (pos < nbits) {
-        const int ncand = min(32, nbits - pos);
-        if (lane < ncand) { float s = __ldg(soft + pos + lane); w[63 + lane] = p.softinv ? -s : s; }
-        __syncwarp();
-        float mv = 0.0f; int hit = 0;
-        if (lane < ncand) {                                                   /* corr_softhdb (demod_mod.c:1692-1716) */
-            double sum = 0.0, normx = 0.0;
+    auto rd = [&](int i) -> float { const float v = i < ncarry ? carry[i] : __ldg(soft + (i - ncarry)); return p.softinv ? -v : v; };
+    int pos = 0, nf = 0, mode = st.mode, byte_count = st.byte_count;
+    long long first_g = st.first_bit; float mvf = st.mv;
+    bool ended = false;
+    while (true) {
+        if (mode == 0) {                                                      /* ---- find_softbinhead (demod_mod.c:1741-1761) ---- */
+            if (pos >= nb) break;
+            const int ncand = min(32, nb - pos);
+            if (lane < ncand) w[63 + lane] = rd(pos + lane);
+            __syncwarp();
+            float mv = 0.0f; int hit = 0;
+            if (lane < ncand) {                                               /* corr_softhdb (demod_mod.c:1692-1716) */
+                double sum = 0.0, normx = 0.0;
 #pragma unroll 8
-            for (int i = 0; i < SS_HEADLEN; ++i) {
-                const float x = w[lane + i], y = c_hdr[i] ? 1.0f : -1.0f;
-                sum += (double)(y * x); normx += (double)(x * x);
+                for (int i = 0; i < SS_HEADLEN; ++i) {
+                    const float x = w[lane + i], y = c_hdr[i] ? 1.0f : -1.0f;
+                    sum += (double)(y * x); normx += (double)(x * x);
+                }
+                mv = (float)(sum / sqrt(normx * 64.0));
+                hit = (fabsf(mv) > 0.7f) && !((double)mv * (0.5 - p.inv) < 0);    /* ths (rs41mod.c:2864) + polarity rule (:2889-2892) */
             }
-            mv = (float)(sum / sqrt(normx * 64.0));
-            hit = (fabsf(mv) > 0.7f) && !((double)mv * (0.5 - p.inv) < 0);    /* ths (rs41mod.c:2864) + polarity rule (:2889-2892) */
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            const int adv = m ? (__ffs(m) - 1) + 1 : ncand;                    /* bits that entered the ring */
+            {   /* slide: the ring keeps the last 63 scanned bits; on a hit it ends at the hit bit (payload never enters it) */
+                const float t0 = w[adv + lane], t1 = (lane + 32 < 63) ? w[adv + lane + 32] : 0.0f;
+                __syncwarp();
+                w[lane] = t0; if (lane + 32 < 63) w[lane + 32] = t1;
+                __syncwarp();
+            }
+            pos += adv;
+            if (!m) continue;
+            mvf = __shfl_sync(0xffffffffu, mv, adv - 1);
+            first_g = base + pos; byte_count = SS_FRAMESTART; mode = 1;
         }
-        const unsigned m = __ballot_sync(0xffffffffu, hit);
-        if (!m) {                                                             /* slide: the ring keeps the last 63 scanned bits */
-            float t0 = w[ncand + lane], t1 = (lane + 32 < 63) ? w[ncand + lane + 32] : 0.0f;
-            __syncwarp();
-            w[lane] = t0; if (lane + 32 < 63) w[lane + 32] = t1;
-            __syncwarp();
-            pos += ncand;
-            continue;
-        }
-        const int f = __ffs(m) - 1;
-        const float mvf = __shfl_sync(0xffffffffu, mv, f);
-        const int first = pos + f + 1;
-        const int nread = min(8 * (SS_FRAME_LEN - SS_FRAMESTART), nbits - first), nby = nread / 8;
-        for (int k = lane; k < nby; k += 32) {                                /* rs41mod.c:2896-2956 */
-            const int bc = SS_FRAMESTART + k; const float *sp = soft + first + 8 * k;
+        /* ---- frame assembly (rs41mod.c:2896-2956): whole bytes only; <8 left-over bits wait for the next push ---- */
+        const int nby = min(SS_FRAME_LEN - byte_count, (nb - pos) / 8);
+        for (int k = lane; k < nby; k += 32) {
+            const int bc = byte_count + k;
             int byte = 0; float mn = 0.0f;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                float s = __ldg(sp + q); if (p.softinv) s = -s;
+                const float s = rd(pos + 8 * k + q);
                 int bit = s >= 0.0f; float sb = s;
                 if (p.inv) { bit ^= 1; sb = -sb; }
                 if (q == 0 || fabsf(sb) < fabsf(mn)) mn = sb;
@@ -257,8 +281,12 @@ __global__ void __launch_bounds__(SS_WARPS * 32) rs41_framesync_kernel(const SsP
             frame[bc] = (unsigned char)(byte ^ c_mask[bc & 63]); score[bc] = mn;
         }
         __syncwarp();
-        const int byte_count = SS_FRAMESTART + nby;
-        if (byte_count < SS_POS_GPS1) { for (int i = byte_count + lane; i < SS_FRAME_LEN; i += 32) frame[i] = 0; __syncwarp(); }   /* print_frame :2481-2484 */
+        byte_count += nby; pos += 8 * nby;
+        if (byte_count < SS_FRAME_LEN) {                                      /* out of bits inside the frame */
+            if (!p.flush) break;                                              /* stream continues: resume here on the next push */
+            ended = true;                                                     /* EOF: an incomplete byte is dropped like the reference's bit loop does */
+            if (byte_count < SS_POS_GPS1) { for (int i = byte_count + lane; i < SS_FRAME_LEN; i += 32) frame[i] = 0; __syncwarp(); }   /* print_frame :2481-2484 */
+        }
         int flen, ec = 0; unsigned crc = 0;
         {
             const unsigned char b = frame[SS_POS_FRAME - 1]; int ft = 0;
@@ -272,19 +300,23 @@ __global__ void __launch_bounds__(SS_WARPS * 32) rs41_framesync_kernel(const SsP
         if (nf < p.maxpc) {
             b200fsk_rs41_frame_t *o = p.frames + (long long)c * p.maxpc + nf;
             for (int i = lane; i < SS_FRAME_LEN; i += 32) { o->bytes[i] = frame[i]; o->bytescore[i] = score[i]; }
-            if (lane == 0) { o->chan = c; o->len = flen; o->nbytes_read = byte_count; o->first_bit = first; o->score = mvf; o->ec = ec; o->crc_mask = (int)crc; }
+            if (lane == 0) { o->chan = c; o->len = flen; o->nbytes_read = byte_count; o->first_bit = first_g; o->score = mvf; o->ec = ec; o->crc_mask = (int)crc; }
         }
-        ++nf;
-        {   /* the header ring is untouched by the payload: it still ends at the hit bit */
-            float t0 = w[f + 1 + lane], t1 = (lane + 32 < 63) ? w[f + 1 + lane + 32] : 0.0f;
-            __syncwarp();
-            w[lane] = t0; if (lane + 32 < 63) w[lane + 32] = t1;
-            __syncwarp();
-        }
-        pos = first + nread;
-        if (pos >= nbits && byte_count < SS_FRAME_LEN) break;                 /* EOF inside the frame */
+        ++nf; mode = 0;
+        if (ended) { pos = nb; break; }                                        /* EOF inside the frame ends the run (rs41mod.c main loop) */
     }
-    if (lane == 0) p.counts[c] = nf;
+    /* save the stream state */
+    const int left = (mode == 1 && !ended) ? nb - pos : 0;                     /* < 8 bits of an unfinished byte */
+    float cv = 0.0f;
+    if (lane < left) { const float v = pos + lane < ncarry ? carry[pos + lane] : __ldg(soft + (pos + lane - ncarry)); cv = v; }   /* raw (un-negated) value */
+    for (int i = lane; i < 63; i += 32) st.ring[i] = w[i];
+    for (int i = lane; i < SS_FRAME_LEN; i += 32) { st.frame[i] = frame[i]; st.score[i] = score[i]; }
+    __syncwarp();
+    if (lane < 8) st.carry[lane] = cv;
+    if (lane == 0) {
+        st.mode = mode; st.byte_count = byte_count; st.ncarry = left; st.consumed = base + nb; st.first_bit = first_g; st.mv = mvf;
+        st.nframes_total += nf; p.counts[c] = nf;
+    }
 }
 
 static thread_local char g_sserr[256];
@@ -293,32 +325,55 @@ extern "C" float b200fsk_framesync_last_kernel_ms(void) { return g_ss_ms; }
 extern "C" const char *b200fsk_framesync_last_error(void) { return g_sserr; }
 #define SCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(g_sserr, sizeof g_sserr, "%s: %s", #call, cudaGetErrorString(e_)); return B200FSK_ECUDA; } } while (0)
 
-extern "C" int b200fsk_rs41_frames_device(const float *d_soft, long stride, const int *d_nbits, int nbits, int nchan, int softinv, int inv, int ecc,
-                                          b200fsk_rs41_frame_t *h_frames, int max_frames, int *nframes, int device, void *stream);
+struct b200fsk_rs41sync { int nchan, softinv, inv, ecc, device; SsState *d_state; b200fsk_rs41_frame_t *d_fr; int *d_cnt; int cap_pc; };
 
-extern "C" int b200fsk_rs41_framesync_device(const float *d_soft, long stride, const int *d_nbits, int nbits, int nchan, int softinv, int inv,
-                                             b200fsk_rs41_frame_t *h_frames, int max_frames, int *nframes, int device, void *stream)
+static int ss_init_tables(void)
 {
-    return b200fsk_rs41_frames_device(d_soft, stride, d_nbits, nbits, nchan, softinv, inv, 0, h_frames, max_frames, nframes, device, stream);
-}
-
-extern "C" int b200fsk_rs41_frames_device(const float *d_soft, long stride, const int *d_nbits, int nbits, int nchan, int softinv, int inv, int ecc,
-                                          b200fsk_rs41_frame_t *h_frames, int max_frames, int *nframes, int device, void *stream)
-{
-    if (!d_soft || !h_frames || !nframes || nchan <= 0 || (nbits < 0) || ecc < 0 || ecc > 2) return B200FSK_EINVAL;
-    SCK(cudaSetDevice(device));
     static bool init = false;
     if (!init) {
         unsigned char hb[64]; for (int i = 0; i < 64; ++i) hb[i] = RS41_HDR[i] & 1;
         SCK(cudaMemcpyToSymbol(c_hdr, hb, 64)); SCK(cudaMemcpyToSymbol(c_mask, RS41_MASK, 64));
         init = true;
     }
-    (void)RS41_HDR_BYTES;
-    const int maxpc = nbits / (8 * (SS_FRAME_LEN - SS_FRAMESTART) + SS_HEADLEN) + 2;
-    b200fsk_rs41_frame_t *d_fr = 0; int *d_cnt = 0;
-    SCK(cudaMalloc(&d_fr, (size_t)nchan * maxpc * sizeof(b200fsk_rs41_frame_t))); SCK(cudaMalloc(&d_cnt, sizeof(int) * nchan));
-    SsParams p; p.soft = d_soft; p.stride = stride; p.nbits_c = d_nbits; p.nbits = nbits; p.nchan = nchan; p.softinv = softinv ? 1 : 0; p.inv = inv ? 1 : 0;
-    p.maxpc = maxpc; p.ecc = ecc; p.frames = d_fr; p.counts = d_cnt;
+    return B200FSK_OK;
+}
+
+extern "C" int b200fsk_rs41sync_create(b200fsk_rs41sync_t **out, int nchan, int softinv, int inv, int ecc, int device)
+{
+    if (!out || nchan <= 0 || ecc < 0 || ecc > 2) return B200FSK_EINVAL;
+    SCK(cudaSetDevice(device));
+    if (int rc = ss_init_tables()) return rc;
+    b200fsk_rs41sync *h = new b200fsk_rs41sync();
+    h->nchan = nchan; h->softinv = softinv ? 1 : 0; h->inv = inv ? 1 : 0; h->ecc = ecc; h->device = device; h->d_fr = 0; h->d_cnt = 0; h->cap_pc = 0;
+    std::vector<SsState> st(nchan);
+    memset(st.data(), 0, sizeof(SsState) * nchan);
+    for (int c = 0; c < nchan; ++c) memcpy(st[c].frame, RS41_HDR_BYTES, 8);                       /* rs41mod.c:2766 */
+    SCK(cudaMalloc(&h->d_state, sizeof(SsState) * nchan));
+    SCK(cudaMemcpy(h->d_state, st.data(), sizeof(SsState) * nchan, cudaMemcpyHostToDevice));
+    SCK(cudaMalloc(&h->d_cnt, sizeof(int) * nchan));
+    *out = h;
+    return B200FSK_OK;
+}
+
+extern "C" void b200fsk_rs41sync_destroy(b200fsk_rs41sync_t *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->d_state) cudaFree(h->d_state); if (h->d_fr) cudaFree(h->d_fr); if (h->d_cnt) cudaFree(h->d_cnt);
+    delete h;
+}
+
+extern "C" int b200fsk_rs41sync_push_device(b200fsk_rs41sync_t *h, const float *d_soft, long stride, const int *d_nbits, int nbits, int flush,
+                                            b200fsk_rs41_frame_t *h_frames, int max_frames, int *nframes, void *stream)
+{
+    if (!h || (!d_soft && nbits > 0) || !h_frames || !nframes || nbits < 0) return B200FSK_EINVAL;
+    SCK(cudaSetDevice(h->device));
+    const int nchan = h->nchan;
+    const int maxpc = nbits / (8 * (SS_FRAME_LEN - SS_FRAMESTART) + SS_HEADLEN) + 3;      /* + the frame in progress + an EOF fragment */
+    if (maxpc > h->cap_pc) { if (h->d_fr) cudaFree(h->d_fr); SCK(cudaMalloc(&h->d_fr, (size_t)nchan * maxpc * sizeof(b200fsk_rs41_frame_t))); h->cap_pc = maxpc; }
+    b200fsk_rs41_frame_t *d_fr = h->d_fr; int *d_cnt = h->d_cnt;
+    SsParams p; p.soft = d_soft; p.stride = stride; p.nbits_c = d_nbits; p.nbits = nbits; p.nchan = nchan; p.softinv = h->softinv; p.inv = h->inv;
+    p.maxpc = maxpc; p.ecc = h->ecc; p.flush = flush ? 1 : 0; p.frames = d_fr; p.counts = d_cnt; p.state = h->d_state;
     cudaStream_t s = (cudaStream_t)stream;
     cudaEvent_t e0, e1; SCK(cudaEventCreate(&e0)); SCK(cudaEventCreate(&e1));
     SCK(cudaEventRecord(e0, s));
@@ -352,6 +407,24 @@ extern "C" int b200fsk_rs41_frames_device(const float *d_soft, long stride, cons
         }
     }
     *nframes = tot;
-    cudaFree(d_fr); cudaFree(d_cnt);
     return B200FSK_OK;
+}
+
+/* whole-buffer calls: one stream per call = create + push(flush) + destroy */
+extern "C" int b200fsk_rs41_frames_device(const float *d_soft, long stride, const int *d_nbits, int nbits, int nchan, int softinv, int inv, int ecc,
+                                          b200fsk_rs41_frame_t *h_frames, int max_frames, int *nframes, int device, void *stream)
+{
+    if (!d_soft || !h_frames || !nframes || nchan <= 0 || (nbits < 0) || ecc < 0 || ecc > 2) return B200FSK_EINVAL;
+    b200fsk_rs41sync_t *h = 0;
+    int rc = b200fsk_rs41sync_create(&h, nchan, softinv, inv, ecc, device);
+    if (rc) return rc;
+    rc = b200fsk_rs41sync_push_device(h, d_soft, stride, d_nbits, nbits, 1, h_frames, max_frames, nframes, stream);
+    b200fsk_rs41sync_destroy(h);
+    return rc;
+}
+
+extern "C" int b200fsk_rs41_framesync_device(const float *d_soft, long stride, const int *d_nbits, int nbits, int nchan, int softinv, int inv,
+                                             b200fsk_rs41_frame_t *h_frames, int max_frames, int *nframes, int device, void *stream)
+{
+    return b200fsk_rs41_frames_device(d_soft, stride, d_nbits, nbits, nchan, softinv, inv, 0, h_frames, max_frames, nframes, device, stream);
 }

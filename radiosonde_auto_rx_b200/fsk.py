@@ -392,6 +392,52 @@ def rs41_framesync_device(d_soft, stride: int, nbits, nchan: int, softinv: bool 
     return [(f.chan, f.len, f.first_bit, f.score, np.frombuffer(bytes(f.bytes), np.uint8)[: f.len].copy(), f.nbytes_read, f.ec, f.crc_mask) for f in fr[: n.value]]
 
 
+class Rs41FrameSync:
+    """Streaming `rs41mod --softin [-i] [--ecc2]` front for ``nchan`` channels: push() soft bits as fsk_demod produces them (device
+    memory), frames come back from the push that completes them; ``flush=True`` on the last push applies the reference's EOF rule."""
+
+    def __init__(self, nchan: int, softinv: bool = False, inv: bool = True, ecc: int = 0, device: int = 0):
+        L = lib()
+        L.b200fsk_rs41sync_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.b200fsk_rs41sync_push_device.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                                   C.POINTER(C.c_int), C.c_void_p]
+        L.b200fsk_rs41sync_destroy.argtypes = [C.c_void_p]
+        L.b200fsk_rs41sync_destroy.restype = None
+        L.b200fsk_framesync_last_error.restype = C.c_char_p
+        self.L, self.nchan, self.h = L, nchan, C.c_void_p()
+        rc = L.b200fsk_rs41sync_create(C.byref(self.h), nchan, int(softinv), int(inv), int(ecc), device)
+        if rc:
+            raise B200Error(f"rs41sync_create error {rc}: {L.b200fsk_framesync_last_error().decode()}")
+
+    def push(self, d_soft, stride: int, nbits, flush: bool = False, stream=None):
+        """-> list of (chan, len, first_bit, score, bytes[len], nbytes_read, ec, crc_mask) completed by this push"""
+        if hasattr(nbits, "data_ptr"):
+            pn, nmax = C.c_void_p(nbits.data_ptr()), int(nbits.max().item())
+        else:
+            pn, nmax = None, int(nbits)
+        cap = self.nchan * (nmax // 4144 + 3)
+        fr = (_Rs41Frame * cap)()
+        n = C.c_int(0)
+        ptr = d_soft.data_ptr() if hasattr(d_soft, "data_ptr") else int(d_soft)
+        st = C.c_void_p(stream.cuda_stream) if stream is not None and hasattr(stream, "cuda_stream") else None
+        rc = self.L.b200fsk_rs41sync_push_device(self.h, C.c_void_p(ptr), stride, pn, nmax, int(flush), fr, cap, C.byref(n), st)
+        if rc:
+            raise B200Error(f"rs41sync_push error {rc}: {self.L.b200fsk_framesync_last_error().decode()}")
+        return [(f.chan, f.len, f.first_bit, f.score, np.frombuffer(bytes(f.bytes), np.uint8)[: f.len].copy(), f.nbytes_read, f.ec, f.crc_mask)
+                for f in fr[: n.value]]
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.b200fsk_rs41sync_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def rs41_framesync_kernel_ms() -> float:
     """Device time of the frame-sync (+ECC) kernel in the most recent rs41_framesync_device call of this thread."""
     L = lib()

@@ -169,3 +169,49 @@ def test_rs41_ecc_on_device(cuda, ecc):
         total += len(mine)
         rescued += sum(1 for g in mine if g[6] > 0)
     assert total >= 70 and rescued >= 20
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ecc", [0, 2])
+def test_rs41_streaming_pushes_equal_whole_buffer(cuda, ecc):
+    """the same streams cut into pushes of arbitrary sizes (1 bit ... several frames, different per channel) through the streaming
+    handle give exactly the frames of the whole-buffer call (and therefore of the oracle / reference): state carried across pushes is
+    the header ring, the frame in progress with its unfinished byte, and the frame buffer the EOF rule falls back on"""
+    import torch
+    from radiosonde_auto_rx_b200 import fsk
+    streams = [rf.soft_stream(s, 8, sg, burst=b)[0] for s, sg, b in CASES[:7]]
+    streams[3] = streams[3][: streams[3].size - 3000]
+    streams[5] = streams[5][: streams[5].size - 1001]              # ends inside a byte of a frame
+    nch = len(streams)
+    n = max(s.size for s in streams)
+    buf = np.zeros((nch, n), np.float32)
+    for i, s in enumerate(streams):
+        buf[i, : s.size] = s
+    nb = torch.tensor([s.size for s in streams], dtype=torch.int32, device="cuda")
+    whole = fsk.rs41_framesync_device(torch.from_numpy(buf).cuda(), n, nb, nch, ecc=ecc)
+    rng = np.random.default_rng(5 + ecc)
+    sync = fsk.Rs41FrameSync(nch, ecc=ecc)
+    pos = np.zeros(nch, np.int64)
+    got, npush = [], 0
+    while True:
+        rem = np.array([s.size for s in streams]) - pos
+        if rem.max() == 0:
+            got += sync.push(torch.zeros((nch, 8), dtype=torch.float32, device="cuda"), 8, 0, flush=True)     # empty push that only flushes
+            break
+        chunk = int(rng.choice([1, 3, 7, 8, 9, 63, 64, 65, 500, 4079, 4080, 4144, 9000, 20000]))
+        take = np.minimum(rem, rng.integers(0, chunk + 1, nch))
+        m = max(int(take.max()), 1)
+        part = np.zeros((nch, m), np.float32)
+        for c in range(nch):
+            part[c, : take[c]] = streams[c][pos[c]: pos[c] + take[c]]
+        got += sync.push(torch.from_numpy(part).cuda(), m, torch.from_numpy(take.astype(np.int32)).cuda())
+        pos += take
+        npush += 1
+    assert npush > 20
+    key = lambda g: (g[0], g[2])
+    got.sort(key=key)
+    whole = sorted(whole, key=key)
+    assert len(got) == len(whole) > 40
+    for g, e in zip(got, whole):
+        assert (g[0], g[1], g[2], g[5], g[6], g[7]) == (e[0], e[1], e[2], e[5], e[6], e[7]), (g[:3], g[5:], e[:3], e[5:])
+        assert g[4].tobytes() == e[4].tobytes() and abs(g[3] - e[3]) < 1e-6
