@@ -27,7 +27,7 @@ def _bits_with_header(rng: np.random.Generator, nbits: int, header: str | None, 
 def fsk_iq(seed: int, nsamp: int, Fs: int = 48000, Rs: int = 4800, M: int = 2,
            f_lo: float | None = None, spacing: float | None = None, ebno_db: float = 15.0,
            ppm: float = 0.0, amp: float = 8000.0, header: str | None = RS41_HEADER,
-           header_period: int = 4800, return_bits: bool = False):
+           header_period: int = 4800, return_bits: bool = False, bits: np.ndarray | None = None):
     """Continuous-phase M-FSK at complex baseband -> cs16 array of shape (nsamp, 2), dtype int16.
 
     Tone m sits at ``f_lo + m*spacing`` Hz.  ``ppm`` stretches the symbol clock, ``ebno_db`` sets
@@ -41,7 +41,12 @@ def fsk_iq(seed: int, nsamp: int, Fs: int = 48000, Rs: int = 4800, M: int = 2,
     bps = 1 if M == 2 else 2
     Ts = Fs / Rs
     nsym = int(nsamp / Ts * (1 + abs(ppm) * 1e-6)) + 4
-    bits = _bits_with_header(rng, nsym * bps, header, header_period)
+    if bits is None:
+        bits = _bits_with_header(rng, nsym * bps, header, header_period)
+    else:                                            # caller-supplied payload (e.g. well-formed RS41 frames); padded with random bits
+        given = np.asarray(bits, dtype=np.uint8)
+        bits = rng.integers(0, 2, size=nsym * bps, dtype=np.uint8)
+        bits[: min(given.size, bits.size)] = given[: bits.size]
     if M == 2:
         sym = bits.astype(np.int64)
     else:
