@@ -61,3 +61,29 @@ def test_dft_oracle_matches_reference_binary(built, kind):
         assert len(dets) > 0 and dets[0][0].startswith(kind[:3]) or kind == "M10"
     for a, b in zip(dets, rdets):
         assert a[0] == b[0] and a[2] == b[2] and abs(a[1] - b[1]) < 1e-3 and abs(a[3] - b[3]) < 0.2
+
+
+@needs_ref
+@pytest.mark.parametrize("sr,bw,hz,dtype", [(2400000, 15.0, 300e3, np.int16), (2400000, 15.0, -500e3, np.uint8), (1000000, 15.0, 200e3, np.float32),
+                                            (960000, 100.0, 100e3, np.int16), (1000000, 15.0, 0.0, np.int16), (48000, 15.0, 0.0, np.int16)])
+def test_dft_wideband_oracle_matches_reference_binary(built, sr, bw, hz, dtype):
+    """`dft_detect --IQ fq`: IF-rate walk-up (1 MHz -> 50 kHz), wide IF (--bw 100 -> 120 kHz, the 60 kHz filter branch), no decimation
+    (sr = 48 kHz: decM 1, 7-tap filter), all three sample formats"""
+    emit = [("RS41", 300e3 if sr > 1e6 else (200e3 if sr == 1000000 else (100e3 if sr == 960000 else 0.0))), ("DFM9", -500e3 if sr > 1e6 else -300e3)]
+    if sr == 48000:
+        emit = [("RS41", 0.0)]
+    wide = siggen.wideband_mix(41, int(sr * 1.3), sr, emit, snr_db=8.0, dc=(120.0, -60.0))
+    if dtype == np.float32:
+        wide = wide.astype(np.float32) / np.float32(32768.0)
+    elif dtype == np.uint8:
+        wide = np.clip(np.rint(wide.astype(np.float32) / 96.0) + 128, 0, 255).astype(np.uint8)
+    bits = {np.int16: 16, np.uint8: 8, np.float32: 32}[dtype]
+    rrc, rdets = po.ref_cli_dft_detect(wide, sr, bw, True, True, bits=bits, fq=hz / sr)
+    rc, dets, info, _ = po.dft_oracle_run_wideband(wide, sr, hz / sr, bw, True, True)
+    assert rc == rrc and len(dets) == len(rdets), (info, rc, rrc, dets, rdets)
+    for a, b in zip(dets, rdets):
+        assert a[0] == b[0] and a[2] == b[2] and abs(a[1] - b[1]) < 1e-3 and abs(a[3] - b[3]) < 0.2
+    if (sr, bw) == (960000, 100.0):
+        assert info["if_sr"] == 120000 and info["decM"] == 8
+    if sr == 48000:
+        assert info["decM"] == 1 and len(dets) > 0
