@@ -41,3 +41,17 @@ def test_bad_configuration_is_an_error_code_not_a_crash(built):
     for kw in (dict(Fs=48000, Rs=4700), dict(Fs=48000, Rs=4800, M=3), dict(Fs=48000, Rs=4800, P=7)):
         with pytest.raises(fsk.B200Error, match="error -1"):
             fsk.FskBatch(**kw)
+
+
+def test_cli_binaries_fail_loudly_without_gpu(built):
+    """the drop-in executables have no CPU path either: without a CUDA device they say so and exit non-zero (no output bytes)"""
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    bin_dir = os.path.join(ROOT, "radiosonde_auto_rx_b200", "bin")
+    for args, msg in ((["fsk_demod", "--cs16", "2", "48000", "4800", "-", "-"], b"no CPU fallback"),
+                      (["dft_detect", "--iq", "--bw", "15", "--dc", "-", "48000", "16"], b"no CPU fallback"),
+                      (["dft_detect", "--IQ", "0.1", "--bw", "15", "-", "2400000", "16"], b"no CPU fallback")):
+        r = subprocess.run([os.path.join(bin_dir, args[0])] + args[1:], input=bytes(4096), capture_output=True, timeout=60)
+        assert r.returncode != 0 and r.stdout == b"" and msg in r.stderr, (args, r.returncode, r.stderr[-200:])
