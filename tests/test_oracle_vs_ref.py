@@ -87,3 +87,38 @@ def test_dft_wideband_oracle_matches_reference_binary(built, sr, bw, hz, dtype):
         assert info["if_sr"] == 120000 and info["decM"] == 8
     if sr == 48000:
         assert info["decM"] == 1 and len(dets) > 0
+
+
+def _random_fsk_config(seed):
+    """a valid modem configuration drawn the way fsk_create_hbr accepts it (utils/fsk.c:120-130: Fs % Rs == 0, (Fs/Rs) % P == 0,
+    P >= 4..., M in {2,4}) with matching signal parameters"""
+    rng = np.random.default_rng(seed)
+    Rs = int(rng.choice([1200, 2400, 2500, 4800, 9600]))
+    Ts = int(rng.choice([8, 10, 16, 20, 40]))
+    Fs = Rs * Ts
+    P = int(rng.choice([p for p in (4, 5, 8, 10, 16, 20) if Ts % p == 0 and p <= Ts]))
+    M = int(rng.choice([2, 4]))
+    Nsym = int(rng.choice([32, 50, 64, 100, 300]))
+    spacing = float(Rs * rng.choice([1.0, 1.5, 2.0]))
+    span = spacing * (M - 1)
+    lim = int(min(Fs // 2 - 1, span + 2 * Rs))
+    mask = int(spacing) if rng.random() < 0.5 else 0
+    cfg = po.FskConfig(Fs, Rs, M, P, Nsym, -lim, lim, mask, soft=bool(rng.random() < 0.7), softinv=bool(rng.random() < 0.3))
+    sig = dict(Fs=Fs, Rs=Rs, M=M, spacing=spacing, ebno_db=float(rng.uniform(6, 16)), ppm=float(rng.uniform(-40, 40)))
+    return cfg, sig
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", range(100, 124))
+def test_fsk_oracle_bit_identical_on_random_configurations(built, seed):
+    """24 seeded modem configurations beyond the production lines (rates, oversampling, P, M, Nsym, estimator, soft/hard/inverted)"""
+    cfg, sig = _random_fsk_config(seed)
+    n = 40 * (cfg.Nsym + 1) * (cfg.Fs // cfg.Rs)
+    iq = siggen.fsk_iq(seed, n, **sig)
+    out, cons, recs = po.Oracle(cfg).run_stream(iq)
+    rout, rcons, rrec, _ = po.ref_run_stream(cfg, iq)
+    assert cons == rcons and len(recs) == len(rrec) > 10, (cfg, cons, rcons)
+    assert out.tobytes() == rout.tobytes(), cfg
+    assert np.array_equal(recs["nin_next"], rrec[:, 1].astype(np.int32))
+    assert np.array_equal(recs["f_est"].view(np.uint32), rrec[:, 6:10].view(np.uint32))
+    assert np.array_equal(recs["snr_est"].view(np.uint32), rrec[:, 5].view(np.uint32))
