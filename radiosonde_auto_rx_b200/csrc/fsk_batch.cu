@@ -20,6 +20,7 @@
 #include <string>
 #include "../../include/b200fsk.h"
 #include "fsk_pipe_kernel.cuh"
+#include "fsk_wpc_kernel.cuh"
 
 static thread_local std::string g_err;
 static int fail(int code, const char *fmt, ...)
@@ -35,6 +36,8 @@ struct b200fsk {
     FskKParams kp;                     /* template of kernel params (tables/state pointers filled) */
     size_t smem;                       /* serial kernel */
     size_t smem_pipe = 0; bool use_pipe = false;   /* pipelined kernel */
+    size_t smem_wpc = 0; bool can_wpc = false, force_wpc = false; int wpc_G = 0, nsm = 0;   /* throughput kernel (many channels per CTA) */
+    float2 *d_fint = 0; int *d_abort = 0; int wpc_thresh = 1 << 30;
     unsigned short *d_invperm = 0;
     std::vector<float> h_fest;         /* LUT: tone estimate in Hz per table index */
     /* device tables */
@@ -95,6 +98,14 @@ static const void *pipe_kernel_fn(int M, int fmt)
     static const pipe_fn_t tab[2][4] = {
         {fsk_demod_pipe_kernel<2, 0>, fsk_demod_pipe_kernel<2, 1>, fsk_demod_pipe_kernel<2, 2>, fsk_demod_pipe_kernel<2, 3>},
         {fsk_demod_pipe_kernel<4, 0>, fsk_demod_pipe_kernel<4, 1>, fsk_demod_pipe_kernel<4, 2>, fsk_demod_pipe_kernel<4, 3>}};
+    return (const void *)tab[M == 4 ? 1 : 0][fmt & 3];
+}
+
+static const void *wpc_kernel_fn(int M, int fmt)
+{
+    static const pipe_fn_t tab[2][4] = {
+        {fsk_wpc_kernel<2, 0>, fsk_wpc_kernel<2, 1>, fsk_wpc_kernel<2, 2>, fsk_wpc_kernel<2, 3>},
+        {fsk_wpc_kernel<4, 0>, fsk_wpc_kernel<4, 1>, fsk_wpc_kernel<4, 2>, fsk_wpc_kernel<4, 3>}};
     return (const void *)tab[M == 4 ? 1 : 0][fmt & 3];
 }
 
@@ -235,6 +246,49 @@ extern "C" int b200fsk_create(b200fsk_t **out, const b200fsk_cfg_t *cfg, int nch
     }
     int maxsmem = 0;
     CK(cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    CK(cudaDeviceGetAttribute(&h->nsm, cudaDevAttrMultiProcessorCount, device));
+    kp.nchan = nchan;
+    {   /* throughput kernel: G channels per CTA (one warp each) + one lane-per-chain oscillator warp; same eligibility as the pipeline */
+        const int nmin = N - Ts / 2, nmax = N + Ts / 2;
+        const int f0 = (int)floor((float)nmin / (Ndft / 2)), f1 = (int)floor((float)nmax / (Ndft / 2));
+        const int Gmax = 32 / M;
+        size_t q = 0;
+        auto takew = [&](size_t bytes) { size_t r = q; q += (bytes + 15) & ~(size_t)15; return (int)r; };
+        kp.w_hann = takew(Ndft * 4); kp.w_tw = takew(Ndft * 8); kp.w_perm = takew(Ndft * 2); kp.w_mask = takew(Ndft * 4);
+        q = (q + 127) & ~(size_t)127; kp.w_chan0 = (int)q;
+        auto layout = [&](int ring, int blk, size_t &stride) {
+            size_t o2 = 0;
+            auto t2 = [&](size_t bytes) { size_t r = o2; o2 += (bytes + 15) & ~(size_t)15; return (int)r; };
+            kp.w_ring_off = t2((size_t)M * (ring + 2) * 8);
+            size_t work = (size_t)WPC_NFB * (Ndft + Ndft / 8) * 8;                /* FFT buffers, time-shared with the timing terms / per-symbol maxima */
+            if (work < (size_t)(blk + 2) * 8) work = (size_t)(blk + 2) * 8;
+            if (work < (size_t)Nsym * 8) work = (size_t)Nsym * 8;
+            kp.w_fft_off = t2(work); kp.w_Sf_off = t2((size_t)2 * Ndft * 4); kp.w_scr_off = t2(Ndft * 4);
+            /* channel stride = 32 B (M=2) / 64 B (M=4) modulo 128: the oscillator's 16-byte stores of a quarter warp hit 8 distinct bank groups */
+            const size_t want = (M == 2) ? 32 : 64;
+            o2 = (o2 + 127) & ~(size_t)127; o2 += want;
+            stride = o2;
+        };
+        int ring = 512, blk = 128; size_t stride = 0;
+        layout(ring, blk, stride);
+        int G = (int)(((size_t)maxsmem - 2048 - kp.w_chan0) / stride);
+        if (G < Gmax && 3 * Ts + 2 * 64 + 16 <= 256) {                            /* smaller ring: more channels per CTA */
+            size_t s2 = 0; layout(256, 64, s2);
+            const int G2 = (int)(((size_t)maxsmem - 2048 - kp.w_chan0) / s2);
+            if (G2 > G) { G = G2; ring = 256; blk = 64; stride = s2; } else layout(ring, blk, stride);
+        }
+        if (G > Gmax) G = Gmax;
+        if (G > WPC_MAXG) G = WPC_MAXG;
+        kp.w_ring = ring; kp.w_blk = blk; kp.w_chan_stride = (int)stride;
+        h->wpc_G = G;
+        h->wpc_thresh = 2 * h->nsm;                               /* above two channels per SM the throughput kernel takes over */
+        if (const char *t = getenv("B200FSK_WPC_THRESH")) h->wpc_thresh = atoi(t);
+        h->can_wpc = (f0 == f1) && (f0 - 1 >= 1) && (3 * Ts + 2 * blk + 16 <= ring) && (nfi >= 2) && (Ndft <= 256) && G >= 1;
+        const char *force = getenv("B200FSK_KERNEL");
+        h->force_wpc = h->can_wpc && force && !strcmp(force, "wpc");
+        if (force && (!strcmp(force, "serial") || !strcmp(force, "pipe"))) h->can_wpc = false;
+        if (force && !strcmp(force, "wpc") && !h->can_wpc) fprintf(stderr, "b200fsk: B200FSK_KERNEL=wpc but this modem is not eligible\n");
+    }
     const bool serial_fits = h->smem + 256 <= (size_t)maxsmem;
     if (h->use_pipe && h->smem_pipe + 1024 > (size_t)maxsmem) h->use_pipe = false;
     if (!h->use_pipe && !serial_fits) { delete h; return fail(B200FSK_ENOMEM, "frame working set %zu B exceeds shared memory %d B", h->smem, maxsmem); }
@@ -245,6 +299,12 @@ extern "C" int b200fsk_create(b200fsk_t **out, const b200fsk_cfg_t *cfg, int nch
             const void *fn = pipe_kernel_fn(M, f);
             CK(allow_max_smem(fn, maxsmem));
         }
+    }
+    if (h->can_wpc) {
+        for (int f = 0; f < 4; ++f) CK(allow_max_smem(wpc_kernel_fn(M, f), maxsmem));
+        CK(zalloc(&h->d_fint, (size_t)nchan * M * nfi));
+        CK(zalloc(&h->d_abort, 1));
+        kp.w_fint = h->d_fint; kp.w_abort = h->d_abort;
     }
 
     std::vector<unsigned short> invperm(Ndft);
@@ -284,7 +344,7 @@ extern "C" void b200fsk_destroy(b200fsk_t *h)
     cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->d_invperm, h->d_hann, h->d_tw, h->d_perm, h->d_phi_ft, h->d_mask, h->d_dphi, h->d_Sf, h->d_phi, h->d_tail, h->d_nrt,
                     h->d_ppm, h->d_nin, h->d_last, h->d_totf, h->d_tots, h->d_nframes, h->d_consumed, h->d_eye, h->d_recs,
-                    h->d_stage[0], h->d_stage[1], h->d_off, h->d_out, h->d_fbase};
+                    h->d_stage[0], h->d_stage[1], h->d_off, h->d_out, h->d_fbase, h->d_fint, h->d_abort};
     for (void *p : ptrs) if (p) cudaFree(p);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaStreamDestroy(h->stream); cudaStreamDestroy(h->copy_stream); cudaStreamDestroy(h->out_stream);
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(h->ev_h2d[i]); cudaEventDestroy(h->ev_k[i]); }
@@ -360,13 +420,37 @@ static int flush_pending(b200fsk *h)
 static int launch(b200fsk *h, FskKParams &kp, cudaStream_t s, bool time_it)
 {
     if (time_it) CK(cudaEventRecord(h->ev0, s));
-    if (h->use_pipe) {
+    /* kernel choice: up to two channels per SM the per-channel pipeline wins (the oscillator recurrence bounds a channel);
+       beyond that the per-sample instruction count decides and the many-channels-per-CTA kernel takes over */
+    const bool wpc = h->can_wpc && (h->force_wpc || h->nchan > h->wpc_thresh);
+    if (wpc) {
+        /* channels per CTA: fill whole waves of one CTA per SM */
+        int G = h->wpc_G;
+        const int per_wave = G * h->nsm, waves = (h->nchan + per_wave - 1) / per_wave;
+        const int Gfit = (h->nchan + waves * h->nsm - 1) / (waves * h->nsm);
+        if (Gfit < G) G = Gfit;
+        if (G < 1) G = 1;
+        kp.w_G = G;
+        const size_t smem = (size_t)kp.w_chan0 + (size_t)G * kp.w_chan_stride;
+        void *args[] = {(void *)&kp};
+        CK(cudaLaunchKernel(wpc_kernel_fn(kp.M, kp.fmt), dim3((h->nchan + G - 1) / G), dim3((G + 1) * 32), args, smem, s));
+    } else if (h->use_pipe) {
         void *args[] = {(void *)&kp};
         CK(cudaLaunchKernel(pipe_kernel_fn(kp.M, kp.fmt), dim3(h->nchan), dim3(PIPE_THREADS), args, h->smem_pipe, s));
     } else fsk_demod_kernel<<<h->nchan, FSK_THREADS, h->smem, s>>>(kp);
     CK(cudaGetLastError());
     if (time_it) { CK(cudaEventRecord(h->ev1, s)); h->timed = true; }
     h->launches++;
+    return 0;
+}
+
+/* the throughput kernel's watchdog: a CTA that waited ~4 s for its own oscillator gives up and raises this flag */
+static int check_abort(b200fsk *h)
+{
+    if (!h->d_abort) return 0;
+    int a = 0;
+    CK(cudaMemcpy(&a, h->d_abort, sizeof a, cudaMemcpyDeviceToHost));
+    if (a) { cudaMemset(h->d_abort, 0, sizeof a); return fail(B200FSK_ECUDA, "fsk_wpc_kernel watchdog: a channel group stalled"); }
     return 0;
 }
 
@@ -400,6 +484,7 @@ extern "C" int b200fsk_counts(b200fsk_t *h, int *frames, long *consumed)
     if (!h) return fail(B200FSK_EINVAL, "null");
     CK(cudaSetDevice(h->device));
     CK(cudaDeviceSynchronize());
+    { const int rc = check_abort(h); if (rc) return rc; }
     if (frames) CK(cudaMemcpy(frames, h->d_nframes, sizeof(int) * h->nchan, cudaMemcpyDeviceToHost));
     if (consumed) {
         std::vector<long long> t(h->nchan);
@@ -523,6 +608,7 @@ extern "C" int b200fsk_push_host(b200fsk_t *h, const void *h_in, int fmt, long i
                              (size_t)(mx - rows_sent) * h->Nbits * oes, nchan, cudaMemcpyDeviceToHost, s));
     }
     CK(cudaStreamSynchronize(h->out_stream));
+    { const int rc2 = check_abort(h); if (rc2) return rc2; }
     if (mx > 0) {
         if (h->stats_on) {
             h->h_recs.resize((size_t)nchan * mx);

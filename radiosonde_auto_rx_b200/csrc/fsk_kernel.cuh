@@ -69,6 +69,10 @@ struct FskKParams {
     FskFrameRec *recs; long long rec_stride; int write_recs;
     int *nframes; long long *consumed; float *eye_raw;
     long long *prof;            /* FSK_PROFILE builds only: per-phase cycle counters [nchan][16] */
+    /* throughput kernel (fsk_wpc_kernel.cuh): channels per CTA, ring geometry, shared-memory byte offsets, global f_int */
+    int nchan, w_G, w_ring, w_blk;
+    int w_hann, w_tw, w_perm, w_mask, w_chan0, w_chan_stride, w_ring_off, w_fft_off, w_Sf_off, w_scr_off;
+    float2 *w_fint; int *w_abort;
 };
 
 __device__ __forceinline__ float2 cmul_rn(float2 a, float2 b)       /* comp_prim.h:57-65 */

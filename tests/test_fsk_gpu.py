@@ -43,7 +43,7 @@ def channels(seed, nchan, nsamp, kw):
     return iq
 
 
-@pytest.mark.parametrize("mode", ["auto", "serial"])
+@pytest.mark.parametrize("mode", ["auto", "serial", "wpc"])
 @pytest.mark.parametrize("name", list(CONFIGS))
 def test_push_matches_oracle(cuda, name, mode):
     cfg, kw = CONFIGS[name]
@@ -70,7 +70,7 @@ def test_push_matches_oracle(cuda, name, mode):
         assert b.Sf(c).tobytes() == orc.Sf().tobytes()
 
 
-@pytest.mark.parametrize("mode", ["auto", "serial"])
+@pytest.mark.parametrize("mode", ["auto", "serial", "wpc"])
 def test_chunked_push_equals_single_push(cuda, mode):
     """Streaming: arbitrary chunking of the input must not change a single output bit (carry logic)."""
     cfg = po.RS41
@@ -90,11 +90,12 @@ def test_chunked_push_equals_single_push(cuda, mode):
         assert np.concatenate(got[c]).tobytes() == ref[c].tobytes()
 
 
-def test_max_frames_cap_and_stats_cadence(cuda):
+@pytest.mark.parametrize("mode", ["auto", "wpc"])
+def test_max_frames_cap_and_stats_cadence(cuda, mode):
     cfg = po.RS41
     iq = channels(11, 1, 60_000, {})
     ref, _, recs = po.Oracle(cfg).run_stream(iq[0])
-    b = make_batch(cfg, 1)
+    b = make_batch(cfg, 1, mode=None if mode == "auto" else mode)
     b.enable_stats(True)
     got, k, pos = [], 0, 0
     while True:
@@ -111,8 +112,9 @@ def test_max_frames_cap_and_stats_cadence(cuda):
     assert np.concatenate(got).tobytes() == ref.tobytes()
 
 
+@pytest.mark.parametrize("mode", ["auto", "wpc"])
 @pytest.mark.parametrize("fmt", ["f32", "cu8", "s16"])
-def test_input_formats(cuda, fmt):
+def test_input_formats(cuda, fmt, mode):
     cfg = po.FskConfig(48000, 4800, 2, 10, 50, lower=(0 if fmt == "s16" else None))
     iq = siggen.fsk_iq(21, 80_000, ebno_db=12)
     if fmt == "f32":
@@ -122,7 +124,7 @@ def test_input_formats(cuda, fmt):
     else:
         data = np.ascontiguousarray(iq[:, 0]).reshape(1, -1)
     ref, _, _ = po.Oracle(cfg).run_stream(data[0], fmt)
-    b = make_batch(cfg, 1)
+    b = make_batch(cfg, 1, mode=None if mode == "auto" else mode)
     out, frames = b.push(data, fmt, soft=True)
     assert frames[0] > 0 and out[0, : frames[0] * b.Nbits].tobytes() == ref.tobytes()
 
@@ -167,13 +169,14 @@ def test_reference_named_api(cuda):
     fsk.fsk_destroy(m)
 
 
-def test_nan_input_follows_reference_early_return(cuda):
+@pytest.mark.parametrize("mode", ["auto", "wpc"])
+def test_nan_input_follows_reference_early_return(cuda, mode):
     """fsk.c:702-704: a NaN timing estimate returns early and the CLI re-emits its stale buffer."""
     cfg = po.FskConfig(48000, 4800, 2, 10, 50, softinv=True)
     x = (siggen.fsk_iq(51, 20_000, ebno_db=15).astype(np.float32) / np.float32(1000)).reshape(-1)
     x[2 * 2100] = np.nan
     ref, _, _ = po.Oracle(cfg).run_stream(x, "f32")
-    b = make_batch(cfg, 1)
+    b = make_batch(cfg, 1, mode=None if mode == "auto" else mode)
     out, frames = b.push(x.reshape(1, -1), "f32", soft=True, softinv=True)
     got = out[0, : frames[0] * b.Nbits]
     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
@@ -216,13 +219,14 @@ def test_mixed_2fsk_4fsk_batch(cuda):
     mb.close()
 
 
-def test_empty_and_sub_frame_pushes(cuda):
+@pytest.mark.parametrize("mode", ["auto", "wpc"])
+def test_empty_and_sub_frame_pushes(cuda, mode):
     """Edge cases of the stream interface: zero-length pushes, pushes shorter than a frame (nothing may come out until a
     whole frame is available), and sample-by-sample feeding around a frame boundary."""
     cfg = po.RS41
     iq = siggen.fsk_iq(91, 12_500, ebno_db=12.0)
     ref, _, recs = po.Oracle(cfg).run_stream(iq)
-    b = make_batch(cfg, 1)
+    b = make_batch(cfg, 1, mode=None if mode == "auto" else mode)
     out, fr = b.push(iq[None, :0], "cs16")
     assert fr[0] == 0
     got = []
@@ -235,14 +239,17 @@ def test_empty_and_sub_frame_pushes(cuda):
     assert np.concatenate(got).tobytes() == ref.tobytes() and len(recs) == 4
 
 
-def test_more_channels_than_resident_ctas(cuda):
+@pytest.mark.parametrize("mode", ["pipe", "auto"])
+def test_more_channels_than_resident_ctas(cuda, mode):
     """600 channels > 2 CTAs x 148 SMs: several waves of channel CTAs, every channel still bit-exact; ragged content
-    (noise-only, different SNR / ppm / offsets) exercises different nin sequences per channel."""
+    (noise-only, different SNR / ppm / offsets) exercises different nin sequences per channel.  'auto' picks the
+    many-channels-per-CTA throughput kernel for this batch size (16 channels share one lane-per-chain oscillator warp),
+    'pipe' keeps the one-CTA-per-channel pipeline running in waves."""
     cfg = po.RS41
     nchan, nsamp = 600, 40_000
     iq = siggen.fsk_batch(5150, nchan, nsamp)
     iq[7] = siggen.noise_iq(1, nsamp); iq[311] = siggen.noise_iq(2, nsamp); iq[599] = siggen.noise_iq(3, nsamp)
-    b = make_batch(cfg, nchan)
+    b = make_batch(cfg, nchan, mode=None if mode == "auto" else mode)
     out, frames = b.push(iq, "cs16")
     for c in list(range(0, nchan, 37)) + [7, 311, 599]:
         ref, _, recs = po.Oracle(cfg).run_stream(iq[c])
