@@ -1,22 +1,28 @@
 #!/usr/bin/env python
-"""Summarise `ncu -i X.ncu-rep --page source --print-source cuda,sass --csv` by CUDA source line:
-share of warp-stall samples and executed warp instructions per line (top N)."""
-import csv, sys
-rows = list(csv.reader(open(sys.argv[1])))
-top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-cur = None; hdr = None; data = []
+"""Per-source-line summary of an ncu capture: usage ncu_lines.py <rep> [top]
+Runs `ncu -i <rep> --page source --print-source cuda,sass --csv` and prints, per CUDA source line, the share of warp
+samples, executed warp-instructions and shared-memory wavefronts."""
+import csv, subprocess, sys, collections, os
+rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 45
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.splitlines()))
+cur_file = None; hdr = None
+agg = collections.defaultdict(lambda: [0, 0, 0, 0, ""])
 for r in rows:
     if not r: continue
-    if r[0] == "File Path": cur = r[1].split("/")[-1]; continue
+    if r[0] == "File Path": cur_file = os.path.basename(r[1]); continue
+    if r[0] == "Function Name": continue
     if r[0] == "Line No": hdr = r; continue
-    if hdr is None or len(r) < 10: continue
-    if r[2] != "-": continue          # keep the per-source-line aggregate rows (Address == '-')
-    try:
-        s = int(r[6]); ie = int(r[7])
-    except ValueError:
-        continue
-    data.append((s, ie, cur, r[0], r[1].strip()[:100]))
-tot = sum(d[0] for d in data); toti = sum(d[1] for d in data)
-print(f"total samples {tot}  total warp-instructions {toti}")
-for s, ie, f, ln, src in sorted(data, reverse=True)[:top]:
-    print(f"{100*s/max(tot,1):5.1f}% smp  {100*ie/max(toti,1):5.1f}% inst  {f}:{ln}: {src}")
+    if hdr is None or not r[0].isdigit(): continue
+    if r[2] != "-": continue                      # SASS rows carry an address; CUDA rows have '-'
+    d = dict(zip(hdr, r))
+    def num(k):
+        try: return float(d.get(k, "0") or 0)
+        except ValueError: return 0.0
+    key = (cur_file, int(r[0]))
+    a = agg[key]
+    a[0] += num("# Samples"); a[1] += num("Instructions Executed"); a[2] += num("L1 Wavefronts Shared"); a[3] += num("L1 Wavefronts Shared Excessive"); a[4] = r[1].strip()[:110]
+ts = sum(a[0] for a in agg.values()) or 1; ti = sum(a[1] for a in agg.values()) or 1; tw = sum(a[2] for a in agg.values()) or 1
+print(f"total samples {ts:.0f}  warp-instructions {ti:.0f}  shared wavefronts {tw:.0f} (excessive {sum(a[3] for a in agg.values()):.0f})")
+for key, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+    print(f"{100*a[0]/ts:5.1f}% smp {100*a[1]/ti:5.1f}% inst {100*a[2]/tw:5.1f}% smemwf (exc {100*a[3]/tw:4.1f}%)  {key[0]}:{key[1]}: {a[4]}")

@@ -261,9 +261,12 @@ extern "C" int b200fsk_create(b200fsk_t **out, const b200fsk_cfg_t *cfg, int nch
             auto t2 = [&](size_t bytes) { size_t r = o2; o2 += (bytes + 15) & ~(size_t)15; return (int)r; };
             kp.w_ring_off = t2((size_t)M * (ring + 2) * 8);
             size_t work = (size_t)WPC_NFB * (Ndft + Ndft / 8) * 8;                /* FFT buffers, time-shared with the timing terms / per-symbol maxima */
-            if (work < (size_t)(blk + 2) * 8) work = (size_t)(blk + 2) * 8;
+            /* outputs one block can complete: blk/step new ones + those that were waiting on the integrator memory (Nmem - nin <= 2.5 Ts) */
+            kp.w_tcap = (blk + 3 * Ts + 8) & ~3;
+            if (work < (size_t)kp.w_tcap * 8) work = (size_t)kp.w_tcap * 8;
             if (work < (size_t)Nsym * 8) work = (size_t)Nsym * 8;
-            kp.w_fft_off = t2(work); kp.w_Sf_off = t2((size_t)2 * Ndft * 4); kp.w_scr_off = t2(Ndft * 4);
+            if (work < (size_t)Ndft * 4) work = (size_t)Ndft * 4;                    /* ... and the estimator scratch */
+            kp.w_fft_off = t2(work); kp.w_Sf_off = t2((size_t)2 * Ndft * 4); kp.w_scr_off = kp.w_fft_off;
             /* channel stride = 32 B (M=2) / 64 B (M=4) modulo 128: the oscillator's 16-byte stores of a quarter warp hit 8 distinct bank groups */
             const size_t want = (M == 2) ? 32 : 64;
             o2 = (o2 + 127) & ~(size_t)127; o2 += want;
@@ -271,10 +274,11 @@ extern "C" int b200fsk_create(b200fsk_t **out, const b200fsk_cfg_t *cfg, int nch
         };
         int ring = 512, blk = 128; size_t stride = 0;
         layout(ring, blk, stride);
-        int G = (int)(((size_t)maxsmem - 2048 - kp.w_chan0) / stride);
+        const size_t budget = (size_t)maxsmem / WPC_CTAS - 2048 - (WPC_CTAS > 1 ? 1024 : 0);
+        int G = (int)((budget - kp.w_chan0) / stride);
         if (G < Gmax && 3 * Ts + 2 * 64 + 16 <= 256) {                            /* smaller ring: more channels per CTA */
             size_t s2 = 0; layout(256, 64, s2);
-            const int G2 = (int)(((size_t)maxsmem - 2048 - kp.w_chan0) / s2);
+            const int G2 = (int)((budget - kp.w_chan0) / s2);
             if (G2 > G) { G = G2; ring = 256; blk = 64; stride = s2; } else layout(ring, blk, stride);
         }
         if (G > Gmax) G = Gmax;
@@ -302,7 +306,11 @@ extern "C" int b200fsk_create(b200fsk_t **out, const b200fsk_cfg_t *cfg, int nch
     }
     if (h->can_wpc) {
         for (int f = 0; f < 4; ++f) CK(allow_max_smem(wpc_kernel_fn(M, f), maxsmem));
-        CK(zalloc(&h->d_fint, (size_t)nchan * M * nfi));
+        {   /* f_int spill: one slot per (SM, channel warp); with WPC_CTAS > 1 two CTAs may share an SM -> fall back to per-channel slots */
+            const int slots = (WPC_CTAS == 1) ? h->nsm : nchan;       /* nchan >= number of CTAs */
+            kp.w_fint_slots = slots;
+            CK(zalloc(&h->d_fint, (size_t)slots * WPC_MAXG * M * nfi));
+        }
         CK(zalloc(&h->d_abort, 1));
         kp.w_fint = h->d_fint; kp.w_abort = h->d_abort;
     }
@@ -426,8 +434,8 @@ static int launch(b200fsk *h, FskKParams &kp, cudaStream_t s, bool time_it)
     if (wpc) {
         /* channels per CTA: fill whole waves of one CTA per SM */
         int G = h->wpc_G;
-        const int per_wave = G * h->nsm, waves = (h->nchan + per_wave - 1) / per_wave;
-        const int Gfit = (h->nchan + waves * h->nsm - 1) / (waves * h->nsm);
+        const int slots = h->nsm * WPC_CTAS, per_wave = G * slots, waves = (h->nchan + per_wave - 1) / per_wave;
+        const int Gfit = (h->nchan + waves * slots - 1) / (waves * slots);
         if (Gfit < G) G = Gfit;
         if (G < 1) G = 1;
         kp.w_G = G;

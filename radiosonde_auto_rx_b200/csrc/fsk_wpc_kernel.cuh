@@ -27,8 +27,15 @@
 #pragma once
 #include "fsk_pipe_kernel.cuh"
 
+#ifndef WPC_MAXG
 #define WPC_MAXG   16           /* channel warps per CTA (32 chains at M = 2) */
-#define WPC_NFB    4            /* FFTs a channel warp advances together */
+#endif
+#ifndef WPC_NFB
+#define WPC_NFB    3            /* FFTs a channel warp advances together */
+#endif
+#ifndef WPC_CTAS
+#define WPC_CTAS   1            /* CTAs per SM the kernel is sized for (registers, shared memory) */
+#endif
 #define WPC_CHUNK  64           /* oscillator steps between position publications */
 #define WPC_SPIN_LIMIT (1LL << 33)   /* watchdog: cycles a wait may last before the CTA gives up (~4 s) */
 
@@ -50,16 +57,18 @@ __device__ __forceinline__ bool wpc_wait_ge(const int *flag, int want, WpcCtl *c
 {
     if (ld_acq(flag) >= want) return true;
     const long long t0 = clock64();
-    while (true) {
+    for (unsigned it = 1;; ++it) {
         __nanosleep(ns);
         if (ld_acq(flag) >= want) return true;
-        if (ld_vol(&ctl->abort)) return false;
-        if (clock64() - t0 > WPC_SPIN_LIMIT) { *(volatile int *)&ctl->abort = 1; return false; }
+        if ((it & 31u) == 0) {                                       /* watchdog and abort only now and then: the loop must stay cheap */
+            if (ld_vol(&ctl->abort)) return false;
+            if (clock64() - t0 > WPC_SPIN_LIMIT) { *(volatile int *)&ctl->abort = 1; return false; }
+        }
     }
 }
 
 template <int M, int FMT>
-__global__ void __launch_bounds__((WPC_MAXG + 1) * 32, 1) fsk_wpc_kernel(const FskKParams p)
+__global__ void __launch_bounds__((WPC_MAXG + 1) * 32, WPC_CTAS) fsk_wpc_kernel(const FskKParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ WpcCtl ctl;
@@ -135,7 +144,7 @@ __global__ void __launch_bounds__((WPC_MAXG + 1) * 32, 1) fsk_wpc_kernel(const F
                     if (!spin_t0) spin_t0 = clock64();
                     if (ld_vol(&ctl.abort)) break;
                     if (clock64() - spin_t0 > WPC_SPIN_LIMIT) { *(volatile int *)&ctl.abort = 1; break; }
-                    __nanosleep(100);
+                    __nanosleep(400);
                     continue;
                 }
                 n = min(n, fit);
@@ -164,10 +173,12 @@ __global__ void __launch_bounds__((WPC_MAXG + 1) * 32, 1) fsk_wpc_kernel(const F
     float2 *ring  = (float2 *)(cb + p.w_ring_off);                   /* [M][RS]: phi from OSC, then f_dc in place */
     float2 *fftb  = (float2 *)(cb + p.w_fft_off);                    /* [WPC_NFB][Ndft + Ndft/8]; time-shared with tbuf / smax */
     float  *Sfbuf = (float *)(cb + p.w_Sf_off);                      /* [2][Ndft]: Sf after frame k lives in buffer k&1 */
-    float  *scr   = (float *)(cb + p.w_scr_off);
-    float2 *tbuf  = fftb;                                            /* timing terms of one block */
+    float  *scr   = (float *)fftb;                                   /* estimator scratch: runs when no FFT is in flight */
+    float  *tre   = (float *)fftb, *tim = tre + p.w_tcap;   /* timing terms of one block, real / imaginary */
     float2 *s_maxs = fftb;                                           /* per symbol (max, sqrt(max)) */
-    float2 *fintg = p.w_fint + (size_t)c * M * nfi;                  /* this channel's f_int in global memory (L2) */
+    unsigned smid; asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    /* this channel's f_int in global memory (L2): one slot per (SM, channel warp), so the hot set is the resident set */
+    float2 *fintg = p.w_fint + ((size_t)(WPC_CTAS == 1 ? smid % (unsigned)p.w_fint_slots : blockIdx.x) * WPC_MAXG + g) * M * nfi;
 
     for (int i = lane; i < Ndft; i += 32) Sfbuf[Ndft + i] = p.Sf[(long long)c * Ndft + i];      /* "after frame -1" -> buffer 1 */
     for (int e = lane; e < M * p.tailcap; e += 32) {                 /* integrator memory -> ring slots [-tailcap, 0) */
@@ -259,6 +270,9 @@ __global__ void __launch_bounds__((WPC_MAXG + 1) * 32, 1) fsk_wpc_kernel(const F
         int round = est_next ? 0 : nrounds;
         int i_done = 0;
         float acc = 0.0f;                                            /* lanes 0/1: re/im of the timing sum (fsk.c:686-698) */
+        float2 xn[4];                                                /* the next block's samples, fetched one block ahead */
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int t = u * 32 + lane; xn[u] = (t < BLK && ck + t < fend) ? load_sample_t<FMT>(p.in, gbase + ck + t) : make_float2(0.0f, 0.0f); }
         for (int s0 = ck; s0 < fend; s0 += BLK) {
             const int cnt = min(BLK, fend - s0);
             /* oscillator output not there yet: spend the time on the next frame's FFTs */
@@ -266,14 +280,18 @@ __global__ void __launch_bounds__((WPC_MAXG + 1) * 32, 1) fsk_wpc_kernel(const F
                 if (round < nrounds) {
                     est_round(ck1, round, Sf_in, Sf_out);
                     if (++round == nrounds) est_finish(k + 1, Sf_out, tab_next);
-                } else if (!wpc_wait_ge(&ctl.oscpos, s0 + cnt, &ctl, 200)) { dead = true; break; }
+                } else if (!wpc_wait_ge(&ctl.oscpos, s0 + cnt, &ctl, 400)) { dead = true; break; }
             }
             if (dead) break;
             /* down-convert in place: f_dc = x * conj(phi)  (fsk.c:648); BLK <= 128: at most 4 samples per lane */
             {
                 float2 xv[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { const int t = u * 32 + lane; xv[u] = t < cnt ? load_sample_t<FMT>(p.in, gbase + s0 + t) : make_float2(0.0f, 0.0f); }
+                for (int u = 0; u < 4; ++u) {
+                    xv[u] = xn[u];
+                    const int t = BLK + u * 32 + lane;
+                    xn[u] = (u * 32 + lane < BLK && s0 + t < fend) ? load_sample_t<FMT>(p.in, gbase + s0 + t) : make_float2(0.0f, 0.0f);
+                }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int t = u * 32 + lane;
@@ -293,28 +311,66 @@ __global__ void __launch_bounds__((WPC_MAXG + 1) * 32, 1) fsk_wpc_kernel(const F
             int i_hi = 0;
             if (mixed_end - base >= Ts) i_hi = min(nfi, (mixed_end - base - Ts) / step + 1);
             const int ni = i_hi - i_done;
+            const bool pair_path = (step == 2) && !(Ts & 1);         /* windows start every 2nd sample: 16-byte loads, no bank conflicts */
+            const int par = base & 1;
             for (int e = lane; e < ni; e += 32) {
                 const int i = i_done + e, a0 = base + i * step;
                 float2 a[M];
 #pragma unroll
                 for (int m = 0; m < M; ++m) a[m] = make_float2(0.0f, 0.0f);
+                if (pair_path && !par) {                             /* a0 even: Ts/2 aligned pairs */
 #pragma unroll 5
-                for (int j = 0; j < Ts; ++j) {
-                    const int slot = (a0 + j) & RMASK;
+                    for (int j = 0; j < Ts; j += 2) {
+                        const int slot = (a0 + j) & RMASK;
 #pragma unroll
-                    for (int m = 0; m < M; ++m) a[m] = cadd_rn(a[m], ring[m * RS + slot]);
+                        for (int m = 0; m < M; ++m) {
+                            const float4 v = *reinterpret_cast<const float4 *>(ring + m * RS + slot);
+                            a[m] = cadd_rn(a[m], make_float2(v.x, v.y)); a[m] = cadd_rn(a[m], make_float2(v.z, v.w));
+                        }
+                    }
+                } else if (pair_path) {                              /* a0 odd: the aligned pairs straddle the window's ends */
+                    {
+                        const int slot = (a0 - 1) & RMASK;
+#pragma unroll
+                        for (int m = 0; m < M; ++m) { const float4 v = *reinterpret_cast<const float4 *>(ring + m * RS + slot); a[m] = cadd_rn(a[m], make_float2(v.z, v.w)); }
+                    }
+#pragma unroll 4
+                    for (int j = 1; j < Ts - 1; j += 2) {
+                        const int slot = (a0 + j) & RMASK;
+#pragma unroll
+                        for (int m = 0; m < M; ++m) {
+                            const float4 v = *reinterpret_cast<const float4 *>(ring + m * RS + slot);
+                            a[m] = cadd_rn(a[m], make_float2(v.x, v.y)); a[m] = cadd_rn(a[m], make_float2(v.z, v.w));
+                        }
+                    }
+                    {
+                        const int slot = (a0 + Ts - 1) & RMASK;
+#pragma unroll
+                        for (int m = 0; m < M; ++m) { const float4 v = *reinterpret_cast<const float4 *>(ring + m * RS + slot); a[m] = cadd_rn(a[m], make_float2(v.x, v.y)); }
+                    }
+                } else {
+#pragma unroll 5
+                    for (int j = 0; j < Ts; ++j) {
+                        const int slot = (a0 + j) & RMASK;
+#pragma unroll
+                        for (int m = 0; m < M; ++m) a[m] = cadd_rn(a[m], ring[m * RS + slot]);
+                    }
                 }
                 float ft1 = 0.0f;
 #pragma unroll
                 for (int m = 0; m < M; ++m) { fintg[(size_t)m * nfi + i] = a[m]; ft1 = __fadd_rn(ft1, mag2_rn(a[m])); }
                 const float2 pf = __ldg(p.phi_ft + i);
-                tbuf[e] = make_float2(__fmul_rn(ft1, pf.x), __fmul_rn(ft1, pf.y));
+                tre[e] = __fmul_rn(ft1, pf.x); tim[e] = __fmul_rn(ft1, pf.y);
             }
             __syncwarp();
-            if (lane < 2) {
-                const float *t = (const float *)tbuf + lane;
-#pragma unroll 8
-                for (int j = 0; j < ni; ++j) acc = __fadd_rn(acc, t[2 * j]);
+            if (lane < 2) {                                          /* lane 0: real parts, lane 1: imaginary parts, in order */
+                const float *t = lane ? tim : tre;
+                int j = 0;
+                for (; j + 4 <= ni; j += 4) {
+                    const float4 v = *reinterpret_cast<const float4 *>(t + j);
+                    acc = __fadd_rn(acc, v.x); acc = __fadd_rn(acc, v.y); acc = __fadd_rn(acc, v.z); acc = __fadd_rn(acc, v.w);
+                }
+                for (; j < ni; ++j) acc = __fadd_rn(acc, t[j]);
             }
             __syncwarp();
             if (lane == 0) *(volatile int *)&ctl.free_[g] = min(base + i_hi * step, fend - p.tailcap);
