@@ -260,7 +260,8 @@ extern "C" int b200fsk_create(b200fsk_t **out, const b200fsk_cfg_t *cfg, int nch
             size_t o2 = 0;
             auto t2 = [&](size_t bytes) { size_t r = o2; o2 += (bytes + 15) & ~(size_t)15; return (int)r; };
             kp.w_ring_off = t2((size_t)M * (ring + 2) * 8);
-            size_t work = (size_t)WPC_NFB * (Ndft + Ndft / 8) * 8;                /* FFT buffers, time-shared with the timing terms / per-symbol maxima */
+            kp.w_fp = (WPC_NFB == 4 && Ndft == 128) ? F128_STRIDE : Ndft + Ndft / 8;
+            size_t work = (size_t)WPC_NFB * kp.w_fp * 8;                /* FFT buffers, time-shared with the timing terms / per-symbol maxima */
             /* outputs one block can complete: blk/step new ones + those that were waiting on the integrator memory (Nmem - nin <= 2.5 Ts) */
             kp.w_tcap = (blk + 3 * Ts + 8) & ~3;
             if (work < (size_t)kp.w_tcap * 8) work = (size_t)kp.w_tcap * 8;

@@ -72,7 +72,7 @@ struct FskKParams {
     /* throughput kernel (fsk_wpc_kernel.cuh): channels per CTA, ring geometry, shared-memory byte offsets, global f_int */
     int nchan, w_G, w_ring, w_blk;
     int w_hann, w_tw, w_perm, w_mask, w_chan0, w_chan_stride, w_ring_off, w_fft_off, w_Sf_off, w_scr_off;
-    float2 *w_fint; int *w_abort; int w_fint_slots, w_tcap;
+    float2 *w_fint; int *w_abort; int w_fint_slots, w_tcap, w_fp;
 };
 
 __device__ __forceinline__ float2 cmul_rn(float2 a, float2 b)       /* comp_prim.h:57-65 */

@@ -26,12 +26,13 @@
  */
 #pragma once
 #include "fsk_pipe_kernel.cuh"
+#include "fsk_fft128.cuh"
 
 #ifndef WPC_MAXG
-#define WPC_MAXG   16           /* channel warps per CTA (32 chains at M = 2) */
+#define WPC_MAXG   15           /* channel warps per CTA: 16 warps = 512 threads leave 128 registers per thread */
 #endif
 #ifndef WPC_NFB
-#define WPC_NFB    3            /* FFTs a channel warp advances together */
+#define WPC_NFB    4            /* FFTs a channel warp advances together */
 #endif
 #ifndef WPC_CTAS
 #define WPC_CTAS   1            /* CTAs per SM the kernel is sized for (registers, shared memory) */
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__((WPC_MAXG + 1) * 32, WPC_CTAS) fsk_wpc_kernel(
     unsigned char *outb = (unsigned char *)p.out + (long long)c * p.out_stride * (p.soft ? 4 : 1);
     const int numffts = (int)floorf(__fdiv_rn((float)nin_min, (float)(Ndft / 2))) - 1;   /* same for all 3 nin (host-checked) */
     const int nrounds = (numffts + WPC_NFB - 1) / WPC_NFB;
-    const int FP = Ndft + (Ndft >> 3);
+    const int FP = p.w_fp;                                           /* float2 per FFT buffer */
     __syncwarp();
 
     int nin = p.nin[c];
@@ -206,8 +207,12 @@ __global__ void __launch_bounds__((WPC_MAXG + 1) * 32, WPC_CTAS) fsk_wpc_kernel(
     }
 
     /* one EST round: windows [r*NFB, r*NFB+NFB) of the frame that starts at fc; Sf_in -> Sf_out (fsk.c:466-503) */
+    F128Lane L128;
+    const bool fused128 = (WPC_NFB == 4) && (Ndft == 128);          /* fsk_fft128.cuh: two register passes, conflict-free */
+    if (fused128) f128_init(L128, s_hann, lane);
     auto est_round = [&](int fc, int r, const float *Sf_in, float *Sf_out) {
         const int j0 = r * WPC_NFB;
+        if (fused128) { est_round128<FMT>(p, gbase + fc, j0, numffts, fftb, s_tw, L128, (r == 0) ? Sf_in : Sf_out, Sf_out, lane); return; }
         float2 *Fq[WPC_NFB];
 #pragma unroll
         for (int q = 0; q < WPC_NFB; ++q) Fq[q] = fftb + q * FP;
