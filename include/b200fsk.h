@@ -170,6 +170,10 @@ float b200fsk_framesync_last_kernel_ms(void);
 long b200fsk_launch_count(const b200fsk_t *h);
 /* device time (ms) of the most recent demod kernel measured with CUDA events on its own stream; <0 if none */
 float b200fsk_last_kernel_ms(b200fsk_t *h);
+/* which frame kernel the handle's most recent launch used: 0 = fsk_demod_kernel (one stage at a time), 1 = fsk_demod_pipe_kernel
+ * (one warp-specialised CTA per channel: <= 2 channels per SM), 2 = fsk_wpc_kernel (up to 15 channels per CTA sharing one
+ * lane-per-chain oscillator warp: large batches); -1 before the first launch.  All three produce identical bits. */
+int b200fsk_last_kernel_kind(const b200fsk_t *h);
 
 #ifdef __cplusplus
 }

@@ -219,6 +219,8 @@ def reflib() -> C.CDLL:
         L.ref_fsk_run_stream.restype = C.c_long
         L.ref_fsk_run_stream.argtypes = [C.c_int] * 9 + [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int,
                                                          C.c_void_p, C.POINTER(C.c_long), C.c_void_p, C.c_long, C.c_void_p]
+        L.ref_fsk_run_stream_passes.restype = C.c_long
+        L.ref_fsk_run_stream_passes.argtypes = L.ref_fsk_run_stream.argtypes + [C.c_int]
         _ref = L
     return _ref
 

@@ -13,18 +13,35 @@
 /* rec layout per frame (floats): nin_used, nin_next, norm_rx_timing, ppm, EbNodB, snr_est, f_est[4] = 10 floats */
 #define REF_REC 10
 
+long ref_fsk_run_stream_passes(int Fs, int Rs, int M, int P, int nsym, int fs_tx, int lower, int upper, int mask,
+                               const void *in, long nsamp, int fmt, int soft, int softinv,
+                               void *out, long *consumed, float *recs, long max_frames, float *Sf_out, int passes);
+
 long ref_fsk_run_stream(int Fs, int Rs, int M, int P, int nsym, int fs_tx, int lower, int upper, int mask,
                         const void *in, long nsamp, int fmt, int soft, int softinv,
                         void *out, long *consumed, float *recs, long max_frames, float *Sf_out)
+{
+    return ref_fsk_run_stream_passes(Fs, Rs, M, P, nsym, fs_tx, lower, upper, mask, in, nsamp, fmt, soft, softinv, out, consumed, recs, max_frames, Sf_out, 1);
+}
+
+/* `passes` > 1: the SAME modem object walks the same buffer `passes` times (each pass restarts at sample 0 and drops the
+ * sub-frame remainder, the modem state carries over) -- what a handle of the batched library does when bench.py launches it
+ * repeatedly on one resident buffer.  out / consumed / recs describe the LAST pass. */
+long ref_fsk_run_stream_passes(int Fs, int Rs, int M, int P, int nsym, int fs_tx, int lower, int upper, int mask,
+                               const void *in, long nsamp, int fmt, int soft, int softinv,
+                               void *out, long *consumed, float *recs, long max_frames, float *Sf_out, int passes)
 {
     struct FSK *fsk = fsk_create_hbr(Fs, Rs, M, P, nsym, 1000, fs_tx);
     struct MODEM_STATS stats;
     fsk_set_freq_est_limits(fsk, lower, upper);
     fsk_set_freq_est_alg(fsk, mask);
     long pos = 0, nf = 0, nb = fsk->Nbits;
+    int pass;
     COMP *mod = (COMP *)malloc(sizeof(COMP) * (fsk->N + 2 * fsk->Ts));
     float *sd = (float *)calloc(nb, sizeof(float));
     uint8_t *bits = (uint8_t *)calloc(nb, 1);
+    for (pass = 0; pass < passes; pass++) {
+    pos = 0; nf = 0;
     while (pos + (long)fsk_nin(fsk) <= nsamp) {
         int nin = fsk_nin(fsk), i;
         if (fmt == 0) {
@@ -55,6 +72,7 @@ long ref_fsk_run_stream(int Fs, int Rs, int M, int P, int nsym, int fs_tx, int l
             for (m = 0; m < 4; m++) r[6 + m] = m < M ? fe[m] : 0;
         }
         pos += nin; nf++;
+    }
     }
     if (consumed) *consumed = pos;
     if (Sf_out) memcpy(Sf_out, fsk->Sf, sizeof(float) * fsk->Ndft);

@@ -58,7 +58,7 @@ struct b200fsk {
     std::vector<float> snr_est, EbNodB; std::vector<FskFrameRec> last_rec; std::vector<char> have_rec;
     std::vector<FskFrameRec> h_recs; std::vector<int> h_nframes;
     cudaStream_t stream = 0; cudaEvent_t ev0 = 0, ev1 = 0; bool timed = false;
-    long launches = 0;
+    long launches = 0; int last_kind = -1;
 };
 
 const char *b200fsk_last_error(void) { return g_err.c_str(); }
@@ -443,10 +443,12 @@ static int launch(b200fsk *h, FskKParams &kp, cudaStream_t s, bool time_it)
         const size_t smem = (size_t)kp.w_chan0 + (size_t)G * kp.w_chan_stride;
         void *args[] = {(void *)&kp};
         CK(cudaLaunchKernel(wpc_kernel_fn(kp.M, kp.fmt), dim3((h->nchan + G - 1) / G), dim3((G + 1) * 32), args, smem, s));
+        h->last_kind = 2;
     } else if (h->use_pipe) {
+        h->last_kind = 1;
         void *args[] = {(void *)&kp};
         CK(cudaLaunchKernel(pipe_kernel_fn(kp.M, kp.fmt), dim3(h->nchan), dim3(PIPE_THREADS), args, h->smem_pipe, s));
-    } else fsk_demod_kernel<<<h->nchan, FSK_THREADS, h->smem, s>>>(kp);
+    } else { fsk_demod_kernel<<<h->nchan, FSK_THREADS, h->smem, s>>>(kp); h->last_kind = 0; }
     CK(cudaGetLastError());
     if (time_it) { CK(cudaEventRecord(h->ev1, s)); h->timed = true; }
     h->launches++;
@@ -694,6 +696,7 @@ extern "C" int b200fsk_prof_read(b200fsk_t *h, long long *out)
 #endif
 
 extern "C" long b200fsk_launch_count(const b200fsk_t *h) { return h ? h->launches : 0; }
+extern "C" int b200fsk_last_kernel_kind(const b200fsk_t *h) { return h ? h->last_kind : -1; }
 
 extern "C" float b200fsk_last_kernel_ms(b200fsk_t *h)
 {

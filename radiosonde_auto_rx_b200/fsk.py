@@ -85,6 +85,7 @@ def lib() -> C.CDLL:
         L.b200fsk_launch_count.restype = C.c_long
         L.b200fsk_last_kernel_ms.argtypes = [C.c_void_p]
         L.b200fsk_last_kernel_ms.restype = C.c_float
+        L.b200fsk_last_kernel_kind.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -230,6 +231,12 @@ class FskBatch:
 
     def last_kernel_ms(self) -> float:
         return float(self.L.b200fsk_last_kernel_ms(self.h))
+
+    KERNEL_NAMES = {-1: "none", 0: "fsk_demod_kernel", 1: "fsk_demod_pipe_kernel", 2: "fsk_wpc_kernel"}
+
+    def last_kernel(self) -> str:
+        """name of the frame kernel the most recent launch used (include/b200fsk.h: b200fsk_last_kernel_kind)"""
+        return self.KERNEL_NAMES[int(self.L.b200fsk_last_kernel_kind(self.h))]
 
 
 # ==================================================================================================
