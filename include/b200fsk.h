@@ -166,6 +166,13 @@ const char *b200fsk_framesync_last_error(void);
 /* device time (ms, CUDA events) of the frame-sync kernel in this thread's most recent call; < 0 if none */
 float b200fsk_framesync_last_kernel_ms(void);
 
+/* fsk_enable_burst_mode / lock_nin of the reference (fsk.c:724: the next nin is not adapted, it stays at its current value) for
+ * every channel of the handle; takes effect with the next launch. */
+int  b200fsk_set_lock_nin(b200fsk_t *h, int on);
+/* the un-normalised eye traces of channel c's last frame (what the reference keeps when fsk_stats_normalise_eye(fsk, 0) was
+ * called, fsk.c:869-903); eye must hold B200FSK_EYE_TR * B200FSK_EYE_IND floats, rows of B200FSK_EYE_IND */
+int  b200fsk_get_eye_raw(b200fsk_t *h, int c, float *eye);
+
 /* kernel launches issued by this handle so far (bench.py's gpu_launches) */
 long b200fsk_launch_count(const b200fsk_t *h);
 /* device time (ms) of the most recent demod kernel measured with CUDA events on its own stream; <0 if none */

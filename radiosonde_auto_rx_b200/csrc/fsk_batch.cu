@@ -695,6 +695,23 @@ extern "C" int b200fsk_prof_read(b200fsk_t *h, long long *out)
 }
 #endif
 
+extern "C" int b200fsk_set_lock_nin(b200fsk_t *h, int on)
+{
+    if (!h) return fail(B200FSK_EINVAL, "null");
+    h->kp.lock_nin = on ? 1 : 0;
+    return B200FSK_OK;
+}
+
+extern "C" int b200fsk_get_eye_raw(b200fsk_t *h, int c, float *eye)
+{
+    if (!h || !eye) return fail(B200FSK_EINVAL, "null");
+    if (c < 0 || c >= h->nchan) return fail(B200FSK_ERANGE, "channel");
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(eye, h->d_eye + (size_t)c * 8 * 160, sizeof(float) * 8 * 160, cudaMemcpyDeviceToHost));
+    return B200FSK_OK;
+}
+
 extern "C" long b200fsk_launch_count(const b200fsk_t *h) { return h ? h->launches : 0; }
 extern "C" int b200fsk_last_kernel_kind(const b200fsk_t *h) { return h ? h->last_kind : -1; }
 

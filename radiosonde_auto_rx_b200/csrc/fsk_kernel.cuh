@@ -68,6 +68,7 @@ struct FskKParams {
     void *out; long long out_stride; int soft, softinv; int *frame_base;
     FskFrameRec *recs; long long rec_stride; int write_recs;
     int *nframes; long long *consumed; float *eye_raw;
+    int lock_nin;               /* fsk.c:724: burst_mode / lock_nin -- the next nin is not adapted */
     long long *prof;            /* FSK_PROFILE builds only: per-phase cycle counters [nchan][16] */
     /* throughput kernel (fsk_wpc_kernel.cuh): channels per CTA, ring geometry, shared-memory byte offsets, global f_int */
     int nchan, w_G, w_ring, w_blk;
@@ -425,7 +426,8 @@ __global__ void __launch_bounds__(FSK_THREADS) fsk_demod_kernel(const FskKParams
                     const float appm = (float)__ddiv_rn(__dmul_rn(1e6, (double)d), (double)(float)nsym);
                     s_ppm = (float)__dadd_rn(__dmul_rn(.9, (double)s_ppm), __dmul_rn(.1, (double)appm));
                 }
-                if (nrt > 0.25f) nin_next = p.N + Ts / 2;
+                if (p.lock_nin) nin_next = nin;
+                else if (nrt > 0.25f) nin_next = p.N + Ts / 2;
                 else if (nrt < -0.25f) nin_next = p.N - Ts / 2;
                 else nin_next = p.N;
                 const int low = (int)floorf(rx_timing);

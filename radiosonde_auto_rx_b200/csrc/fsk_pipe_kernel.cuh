@@ -360,7 +360,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
                     const float appm = (float)__ddiv_rn(__dmul_rn(1e6, (double)d), (double)(float)nsym);
                     ppm = (float)__dadd_rn(__dmul_rn(.9, (double)ppm), __dmul_rn(.1, (double)appm));
                 }
-                if (nrt > 0.25f) nin_next = p.N + Ts / 2;
+                if (p.lock_nin) nin_next = nin;
+                else if (nrt > 0.25f) nin_next = p.N + Ts / 2;
                 else if (nrt < -0.25f) nin_next = p.N - Ts / 2;
                 else nin_next = p.N;
                 low = (int)floorf(rx_timing); fract = __fsub_rn(rx_timing, (float)low); high = (int)ceilf(rx_timing);

@@ -405,7 +405,8 @@ __global__ void __launch_bounds__((WPC_MAXG + 1) * 32, WPC_CTAS) fsk_wpc_kernel(
                 const float appm = (float)__ddiv_rn(__dmul_rn(1e6, (double)dd), (double)(float)nsym);
                 ppm = (float)__dadd_rn(__dmul_rn(.9, (double)ppm), __dmul_rn(.1, (double)appm));
             }
-            if (nrt > 0.25f) nin_next = p.N + Ts / 2;
+            if (p.lock_nin) nin_next = nin;
+            else if (nrt > 0.25f) nin_next = p.N + Ts / 2;
             else if (nrt < -0.25f) nin_next = p.N - Ts / 2;
             else nin_next = p.N;
             low = (int)floorf(rx_timing); fract = __fsub_rn(rx_timing, (float)low); high = (int)ceilf(rx_timing);
