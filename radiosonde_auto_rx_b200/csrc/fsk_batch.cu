@@ -28,6 +28,8 @@ static int fail(int code, const char *fmt, ...)
     char buf[512]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
     g_err = buf; return code;
 }
+/* inside b200fsk_create, once the handle exists: a failure releases everything allocated so far */
+#define CKH(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { b200fsk_destroy(h); return fail(B200FSK_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); } } while (0)
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(B200FSK_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
 
 struct b200fsk {
@@ -132,6 +134,8 @@ template <class T> static cudaError_t zalloc(T **dptr, size_t n)
     return cudaMemset(*dptr, 0, n * sizeof(T));
 }
 
+extern "C" void b200fsk_destroy(b200fsk_t *h);
+
 extern "C" int b200fsk_create(b200fsk_t **out, const b200fsk_cfg_t *cfg, int nchan, int device)
 {
     if (!out || !cfg || nchan <= 0) return fail(B200FSK_EINVAL, "bad arguments");
@@ -154,7 +158,7 @@ extern "C" int b200fsk_create(b200fsk_t **out, const b200fsk_cfg_t *cfg, int nch
     float Ndft_f = (float)Fs / bin_width_Hz;
     Ndft_f = pow(2.0, ceil(log2(Ndft_f)));
     const int Ndft = (int)Ndft_f, Ts = Fs / Rs, N = Ts * Nsym, Nmem = N + 2 * Ts, nfi = (Nsym + 1) * P;
-    if (Ndft < 4 || Ndft > 4096) { delete h; return fail(B200FSK_EINVAL, "Ndft=%d unsupported", Ndft); }
+    if (Ndft < 4 || Ndft > 4096) { b200fsk_destroy(h); return fail(B200FSK_EINVAL, "Ndft=%d unsupported", Ndft); }
     h->Ts = Ts; h->N = N; h->Nmem = Nmem; h->Ndft = Ndft; h->nfi = nfi; h->Nbits = (M == 2) ? Nsym : 2 * Nsym;
     h->ncap = N + Ts / 2; h->tailcap = 2 * Ts + Ts / 2; h->xcap = h->ncap > nfi ? h->ncap : nfi;
 
@@ -171,7 +175,7 @@ extern "C" int b200fsk_create(b200fsk_t **out, const b200fsk_cfg_t *cfg, int nch
     kp.neyesamp = (P * 2) / kp.eye_dec; kp.eye_traces = B200FSK_EYE_TR / M;
 
     std::vector<unsigned short> perm;
-    if (plan_fft(Ndft, kp, perm)) { delete h; return fail(B200FSK_EINVAL, "FFT plan"); }
+    if (plan_fft(Ndft, kp, perm)) { b200fsk_destroy(h); return fail(B200FSK_EINVAL, "FFT plan"); }
     std::vector<float> hann(Ndft), mask(Ndft, 0.0f);
     std::vector<float2> tw(Ndft), phi_ft(nfi);
     for (int i = 0; i < Ndft; ++i) hann[i] = 0.5 - 0.5 * cosf(2.0 * M_PI * (float)i / (float)(Ndft - 1));   /* fsk.c:96 */
@@ -245,8 +249,8 @@ extern "C" int b200fsk_create(b200fsk_t **out, const b200fsk_cfg_t *cfg, int nch
         if (force && !strcmp(force, "serial")) h->use_pipe = false;
     }
     int maxsmem = 0;
-    CK(cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-    CK(cudaDeviceGetAttribute(&h->nsm, cudaDevAttrMultiProcessorCount, device));
+    CKH(cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    CKH(cudaDeviceGetAttribute(&h->nsm, cudaDevAttrMultiProcessorCount, device));
     kp.nchan = nchan;
     {   /* throughput kernel: G channels per CTA (one warp each) + one lane-per-chain oscillator warp; same eligibility as the pipeline */
         const int nmin = N - Ts / 2, nmax = N + Ts / 2;
@@ -296,39 +300,39 @@ extern "C" int b200fsk_create(b200fsk_t **out, const b200fsk_cfg_t *cfg, int nch
     }
     const bool serial_fits = h->smem + 256 <= (size_t)maxsmem;
     if (h->use_pipe && h->smem_pipe + 1024 > (size_t)maxsmem) h->use_pipe = false;
-    if (!h->use_pipe && !serial_fits) { delete h; return fail(B200FSK_ENOMEM, "frame working set %zu B exceeds shared memory %d B", h->smem, maxsmem); }
+    if (!h->use_pipe && !serial_fits) { b200fsk_destroy(h); return fail(B200FSK_ENOMEM, "frame working set %zu B exceeds shared memory %d B", h->smem, maxsmem); }
     /* the attribute is per function, not per handle: always allow the device maximum so handles of different sizes coexist */
-    CK(allow_max_smem((const void *)fsk_demod_kernel, maxsmem));
+    CKH(allow_max_smem((const void *)fsk_demod_kernel, maxsmem));
     if (h->use_pipe) {
         for (int f = 0; f < 4; ++f) {
             const void *fn = pipe_kernel_fn(M, f);
-            CK(allow_max_smem(fn, maxsmem));
+            CKH(allow_max_smem(fn, maxsmem));
         }
     }
     if (h->can_wpc) {
-        for (int f = 0; f < 4; ++f) CK(allow_max_smem(wpc_kernel_fn(M, f), maxsmem));
+        for (int f = 0; f < 4; ++f) CKH(allow_max_smem(wpc_kernel_fn(M, f), maxsmem));
         {   /* f_int spill: one slot per (SM, channel warp); with WPC_CTAS > 1 two CTAs may share an SM -> fall back to per-channel slots */
             const int slots = (WPC_CTAS == 1) ? h->nsm : nchan;       /* nchan >= number of CTAs */
             kp.w_fint_slots = slots;
-            CK(zalloc(&h->d_fint, (size_t)slots * WPC_MAXG * M * nfi));
+            CKH(zalloc(&h->d_fint, (size_t)slots * WPC_MAXG * M * nfi));
         }
-        CK(zalloc(&h->d_abort, 1));
+        CKH(zalloc(&h->d_abort, 1));
         kp.w_fint = h->d_fint; kp.w_abort = h->d_abort;
     }
 
     std::vector<unsigned short> invperm(Ndft);
     for (int pos = 0; pos < Ndft; ++pos) invperm[perm[pos]] = (unsigned short)pos;
-    CK(upload(&h->d_invperm, invperm));
-    CK(upload(&h->d_hann, hann)); CK(upload(&h->d_tw, tw)); CK(upload(&h->d_perm, perm));
-    CK(upload(&h->d_phi_ft, phi_ft)); CK(upload(&h->d_mask, mask)); CK(upload(&h->d_dphi, dphi));
-    CK(zalloc(&h->d_Sf, (size_t)nchan * Ndft)); CK(zalloc(&h->d_tail, (size_t)nchan * M * h->tailcap));
-    CK(zalloc(&h->d_nrt, nchan)); CK(zalloc(&h->d_ppm, nchan)); CK(zalloc(&h->d_last, (size_t)nchan * h->Nbits));
-    CK(zalloc(&h->d_totf, nchan)); CK(zalloc(&h->d_tots, nchan)); CK(zalloc(&h->d_nframes, nchan)); CK(zalloc(&h->d_consumed, nchan));
-    CK(zalloc(&h->d_eye, (size_t)nchan * 8 * 160)); CK(zalloc(&h->d_off, (size_t)2 * nchan));
+    CKH(upload(&h->d_invperm, invperm));
+    CKH(upload(&h->d_hann, hann)); CKH(upload(&h->d_tw, tw)); CKH(upload(&h->d_perm, perm));
+    CKH(upload(&h->d_phi_ft, phi_ft)); CKH(upload(&h->d_mask, mask)); CKH(upload(&h->d_dphi, dphi));
+    CKH(zalloc(&h->d_Sf, (size_t)nchan * Ndft)); CKH(zalloc(&h->d_tail, (size_t)nchan * M * h->tailcap));
+    CKH(zalloc(&h->d_nrt, nchan)); CKH(zalloc(&h->d_ppm, nchan)); CKH(zalloc(&h->d_last, (size_t)nchan * h->Nbits));
+    CKH(zalloc(&h->d_totf, nchan)); CKH(zalloc(&h->d_tots, nchan)); CKH(zalloc(&h->d_nframes, nchan)); CKH(zalloc(&h->d_consumed, nchan));
+    CKH(zalloc(&h->d_eye, (size_t)nchan * 8 * 160)); CKH(zalloc(&h->d_off, (size_t)2 * nchan));
     {
         std::vector<float2> phi((size_t)nchan * 4, make_float2(cosf(0), sinf(0)));   /* comp_exp_j(0), fsk.c:164 */
         std::vector<int> nin(nchan, N);
-        CK(upload(&h->d_phi, phi)); CK(upload(&h->d_nin, nin));
+        CKH(upload(&h->d_phi, phi)); CKH(upload(&h->d_nin, nin));
     }
     kp.hann = h->d_hann; kp.tw = h->d_tw; kp.perm = h->d_perm; kp.phi_ft = h->d_phi_ft; kp.mask = h->d_mask; kp.dphi_tab = h->d_dphi; kp.invperm = h->d_invperm;
     kp.Sf = h->d_Sf; kp.phi_c = h->d_phi; kp.fdc_tail = h->d_tail; kp.nrt = h->d_nrt; kp.ppm = h->d_ppm; kp.nin = h->d_nin;
@@ -336,12 +340,12 @@ extern "C" int b200fsk_create(b200fsk_t **out, const b200fsk_cfg_t *cfg, int nch
     kp.nframes = h->d_nframes; kp.consumed = h->d_consumed; kp.eye_raw = h->d_eye;
     h->snr_est.assign(nchan, 0.0f); h->EbNodB.assign(nchan, 0.0f); h->last_rec.resize(nchan); h->have_rec.assign(nchan, 0);
     h->h_tail.assign(nchan, 0); h->h_nframes.assign(nchan, 0);
-    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking));
-    CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1));
-    for (int i = 0; i < 2; ++i) { CK(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming)); }
-    CK(zalloc(&h->d_fbase, nchan));
+    CKH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CKH(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CKH(cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking));
+    CKH(cudaEventCreate(&h->ev0)); CKH(cudaEventCreate(&h->ev1));
+    for (int i = 0; i < 2; ++i) { CKH(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming)); CKH(cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming)); }
+    CKH(zalloc(&h->d_fbase, nchan));
     *out = h;
     return B200FSK_OK;
 }
@@ -350,13 +354,18 @@ extern "C" void b200fsk_destroy(b200fsk_t *h)
 {
     if (!h) return;
     cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
+    if (h->stream) cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->d_invperm, h->d_hann, h->d_tw, h->d_perm, h->d_phi_ft, h->d_mask, h->d_dphi, h->d_Sf, h->d_phi, h->d_tail, h->d_nrt,
                     h->d_ppm, h->d_nin, h->d_last, h->d_totf, h->d_tots, h->d_nframes, h->d_consumed, h->d_eye, h->d_recs,
                     h->d_stage[0], h->d_stage[1], h->d_off, h->d_out, h->d_fbase, h->d_fint, h->d_abort};
     for (void *p : ptrs) if (p) cudaFree(p);
-    cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaStreamDestroy(h->stream); cudaStreamDestroy(h->copy_stream); cudaStreamDestroy(h->out_stream);
-    for (int i = 0; i < 2; ++i) { cudaEventDestroy(h->ev_h2d[i]); cudaEventDestroy(h->ev_k[i]); }
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->out_stream) cudaStreamDestroy(h->out_stream);
+    for (int i = 0; i < 2; ++i) { if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]); if (h->ev_k[i]) cudaEventDestroy(h->ev_k[i]); }
+    cudaGetLastError();
     delete h;
 }
 
@@ -471,6 +480,7 @@ extern "C" int b200fsk_demod_device(b200fsk_t *h, const void *d_in, int fmt, lon
 {
     if (!h || !d_in || !d_out) return fail(B200FSK_EINVAL, "null pointer");
     if (fmt < 0 || fmt > 3 || nsamp < 0) return fail(B200FSK_ERANGE, "fmt/nsamp");
+    if (nsamp > 0x7fff0000L) return fail(B200FSK_ERANGE, "nsamp %ld per channel exceeds the kernels' 31-bit sample index: split the stream", nsamp);
     CK(cudaSetDevice(h->device));
     int rc = flush_pending(h); if (rc) return rc;
     const long long maxf = max_frames > 0 ? max_frames : b200fsk_max_frames(h, nsamp);

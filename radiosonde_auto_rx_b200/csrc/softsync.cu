@@ -327,14 +327,13 @@ extern "C" const char *b200fsk_framesync_last_error(void) { return g_sserr; }
 
 struct b200fsk_rs41sync { int nchan, softinv, inv, ecc, device; SsState *d_state; b200fsk_rs41_frame_t *d_fr; int *d_cnt; int cap_pc; };
 
+/* __constant__ symbols exist once PER DEVICE: upload the 128 bytes on every call for the device that is current (cudaSetDevice by the
+   caller).  A once-per-process flag left every GPU but the first with all-zero header bits and de-whitening mask, and raced between
+   threads. */
 static int ss_init_tables(void)
 {
-    static bool init = false;
-    if (!init) {
-        unsigned char hb[64]; for (int i = 0; i < 64; ++i) hb[i] = RS41_HDR[i] & 1;
-        SCK(cudaMemcpyToSymbol(c_hdr, hb, 64)); SCK(cudaMemcpyToSymbol(c_mask, RS41_MASK, 64));
-        init = true;
-    }
+    unsigned char hb[64]; for (int i = 0; i < 64; ++i) hb[i] = RS41_HDR[i] & 1;
+    SCK(cudaMemcpyToSymbol(c_hdr, hb, 64)); SCK(cudaMemcpyToSymbol(c_mask, RS41_MASK, 64));
     return B200FSK_OK;
 }
 
