@@ -239,7 +239,8 @@ extern "C" int b200fsk_create(b200fsk_t **out, const b200fsk_cfg_t *cfg, int nch
         size_t q = 0;
         auto takeq = [&](size_t bytes) { size_t r = q; q += (bytes + 15) & ~(size_t)15; return (int)r; };
         kp.q_ring = takeq((size_t)M * PIPE_R * 8); kp.q_fint = takeq((size_t)2 * M * nfi * 8); kp.q_stage_bytes = 2 * M * nfi * 8;
-        kp.q_fft = takeq((size_t)PIPE_NEST * PIPE_NFB * (Ndft + Ndft / 8) * 8); kp.q_mag = takeq((size_t)(f0 > 1 ? f0 - 1 : 1) * Ndft * 4);
+        kp.q_fft = takeq((size_t)PIPE_NEST * (Ndft == 128 ? 4 * F128_STRIDE : PIPE_NFB * (Ndft + Ndft / 8)) * 8);
+        kp.q_mag = takeq(Ndft == 128 ? (size_t)4 * PIPE_NEST * F128_MSTRIDE * 4 : (size_t)(f0 > 1 ? f0 - 1 : 1) * Ndft * 4);
         kp.q_Sf = takeq((size_t)2 * Ndft * 4); kp.q_hann = takeq(Ndft * 4); kp.q_tw = takeq(Ndft * 8); kp.q_perm = takeq(Ndft * 2);
         kp.q_scr = takeq(Ndft * 4); kp.q_mask = takeq(Ndft * 4); kp.q_smax = takeq((size_t)Nsym * 8); kp.q_tbuf = takeq(PIPE_TB * 8);
         h->smem_pipe = q;

@@ -19,6 +19,7 @@
 #pragma once
 #include "fsk_kernel.cuh"
 
+#define F128_MSTRIDE 136         /* floats per |X| row when the magnitudes go to a per-frame buffer (MAGOUT) */
 #define F128_STRIDE 152          /* float2 per FFT buffer: 144 (i + i/8 padding) + 8, so that buffers q and q+1 sit 16 banks apart */
 
 __device__ __forceinline__ void kf_bfly2_rn(float2 &X0, float2 &X1, const float2 w)
@@ -60,9 +61,11 @@ __device__ __forceinline__ void f128_init(F128Lane &L, const float *s_hann, int 
 
 /* Windows j0 .. j0+3 of the frame whose first sample is in[gpos]: Hann, FFT, |X|, then Sf_out[i] = IIR over those windows of
  * Sf_src[i] (fsk.c:466-503).  F: 4 buffers of F128_STRIDE float2.  Windows >= numffts are skipped. */
-template <int FMT>
+/* MAGOUT = false: as described.  MAGOUT = true (the per-channel pipeline, where several warps share a frame's windows): |X| of
+ * window j goes to magout[j * mstride + bin] (mstride = 136: rows 8 banks apart) and the caller runs the ordered recursion. */
+template <int FMT, bool MAGOUT = false>
 __device__ __forceinline__ void est_round128(const FskKParams &p, long long gpos, int j0, int numffts, float2 *F, const float2 *s_tw,
-                                             const F128Lane &L, const float *Sf_src, float *Sf_out, int lane)
+                                             const F128Lane &L, const float *Sf_src, float *Sf_out, int lane, float *magout = nullptr)
 {
     /* ---- pass 1: blocks (q, B) with B = lane & 15, q = lane >> 4 and (lane >> 4) + 2 ---- */
     const int B = lane & 15, qa = lane >> 4;
@@ -106,6 +109,15 @@ __device__ __forceinline__ void est_round128(const FskKParams &p, long long gpos
     for (int jj = 0; jj < 4; ++jj) {                                 /* radix 4, m = 32: butterfly v = u + 8 jj, tw[v k] */
         const int v = u + 8 * jj;
         kf_bfly4_rn(y[jj], y[jj + 4], y[jj + 8], y[jj + 12], s_tw[v], s_tw[2 * v], s_tw[3 * v]);
+    }
+    if (MAGOUT) {
+        if (j0 + q < numffts) {
+            float *mag = magout + (j0 + q) * F128_MSTRIDE + u;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) mag[8 * j] = __fsqrt_rn(mag2_rn(y[j]));
+        }
+        __syncwarp();
+        return;
     }
     {
         float *mag = (float *)(F + q * F128_STRIDE) + 8 * q + u;      /* +8 q: the four FFTs' rows land in four different bank octets */

@@ -27,6 +27,7 @@
  */
 #pragma once
 #include "fsk_kernel.cuh"
+#include "fsk_fft128.cuh"
 
 #ifdef FSK_PROFILE
 #define PTIC long long pt_ = clock64();
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
     float  *scr    = (float *)(smem + p.q_scr);
     float  *s_mask = (float *)(smem + p.q_mask);
     float2 *s_maxs = (float2 *)(smem + p.q_smax);
-    float2 *tbuf   = (float2 *)(smem + p.q_tbuf);     /* [PIPE_TB] timing terms of one batch */
+    float  *tre    = (float *)(smem + p.q_tbuf), *tim = tre + PIPE_TB;     /* [PIPE_TB] timing terms of one batch, real / imaginary */
 
     /* ---- prologue ---- */
 #pragma unroll 1
@@ -333,18 +334,23 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
                 if (lane < cnt) {
                     float ft1 = 0.0f;
                     for (int m = 0; m < M; ++m) ft1 = __fadd_rn(ft1, mag2_rn(fint[m * nfi + i0 + lane]));
-                    tbuf[lane] = make_float2(__fmul_rn(ft1, q0.x), __fmul_rn(ft1, q0.y));
+                    tre[lane] = __fmul_rn(ft1, q0.x); tim[lane] = __fmul_rn(ft1, q0.y);
                 }
                 if (lane + 32 < cnt) {
                     float ft1 = 0.0f;
                     for (int m = 0; m < M; ++m) ft1 = __fadd_rn(ft1, mag2_rn(fint[m * nfi + i0 + lane + 32]));
-                    tbuf[lane + 32] = make_float2(__fmul_rn(ft1, q1.x), __fmul_rn(ft1, q1.y));
+                    tre[lane + 32] = __fmul_rn(ft1, q1.x); tim[lane + 32] = __fmul_rn(ft1, q1.y);
                 }
                 __syncwarp();
-                if (lane < 2) {
-                    const float *t = (const float *)tbuf + lane;
-#pragma unroll 16
-                    for (int j = 0; j < cnt; ++j) acc = __fadd_rn(acc, t[2 * j]);
+                if (lane < 2) {                                          /* lane 0: real parts, lane 1: imaginary parts, in order */
+                    const float *t = lane ? tim : tre;
+                    int j = 0;
+#pragma unroll 4
+                    for (; j + 4 <= cnt; j += 4) {
+                        const float4 v = *reinterpret_cast<const float4 *>(t + j);
+                        acc = __fadd_rn(acc, v.x); acc = __fadd_rn(acc, v.y); acc = __fadd_rn(acc, v.z); acc = __fadd_rn(acc, v.w);
+                    }
+                    for (; j < cnt; ++j) acc = __fadd_rn(acc, t[j]);
                 }
                 __syncwarp();
             }
@@ -496,12 +502,34 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
                 int i_hi = 0;
                 if (mixed_end - base >= Ts) i_hi = min(nfi, (mixed_end - base - Ts) / step + 1);
                 const int ni = i_hi - i_done;
-                for (int e = ct; e < (ni << lgM); e += NCT) {            /* fsk.c:660-668 */
-                    const int m = e & (M - 1), i = i_done + (e >> lgM);
+                /* fsk.c:660-668.  Threads are grouped by tone (a warp reads one ring row at consecutive window starts: no bank
+                   conflicts); with windows every 2nd sample the Ts sequential adds take their operands as 16-byte pairs. */
+                const bool pair_path = (step == 2) && !(Ts & 1);
+                const int par = base & 1;
+                for (int e = ct; e < (ni << lgM); e += NCT) {
+                    int m, ii;
+                    if (M == 2) { m = e >= ni ? 1 : 0; ii = e - m * ni; } else { m = e / ni; ii = e - m * ni; }
+                    const int i = i_done + ii, a0 = base + i * step;
                     const float2 *rg = ring + m * PIPE_R;
-                    const int a0 = base + i * step;
                     float2 acc = make_float2(0.0f, 0.0f);
-                    for (int j = 0; j < Ts; ++j) acc = cadd_rn(acc, rg[(a0 + j) & (PIPE_R - 1)]);
+                    if (pair_path && !par) {
+#pragma unroll 5
+                        for (int j = 0; j < Ts; j += 2) {
+                            const float4 v = *reinterpret_cast<const float4 *>(rg + ((a0 + j) & (PIPE_R - 1)));
+                            acc = cadd_rn(acc, make_float2(v.x, v.y)); acc = cadd_rn(acc, make_float2(v.z, v.w));
+                        }
+                    } else if (pair_path) {
+                        { const float4 v = *reinterpret_cast<const float4 *>(rg + ((a0 - 1) & (PIPE_R - 1))); acc = cadd_rn(acc, make_float2(v.z, v.w)); }
+#pragma unroll 4
+                        for (int j = 1; j < Ts - 1; j += 2) {
+                            const float4 v = *reinterpret_cast<const float4 *>(rg + ((a0 + j) & (PIPE_R - 1)));
+                            acc = cadd_rn(acc, make_float2(v.x, v.y)); acc = cadd_rn(acc, make_float2(v.z, v.w));
+                        }
+                        { const float4 v = *reinterpret_cast<const float4 *>(rg + ((a0 + Ts - 1) & (PIPE_R - 1))); acc = cadd_rn(acc, make_float2(v.x, v.y)); }
+                    } else {
+#pragma unroll 5
+                        for (int j = 0; j < Ts; ++j) acc = cadd_rn(acc, rg[(a0 + j) & (PIPE_R - 1)]);
+                    }
                     fint[m * nfi + i] = acc;
                 }
                 group_bar(2, NCT);
@@ -518,7 +546,11 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
         const int ew = ridx;
         const int et = ew * 32 + lane, NET = PIPE_NEST * 32;
         const int numffts = (int)floorf(__fdiv_rn((float)nin_min, (float)(Ndft / 2))) - 1;   /* same for all 3 nin (host-checked) */
-        float2 *F = fftbuf + ew * PIPE_NFB * (Ndft + (Ndft >> 3));       /* PIPE_NFB padded buffers: i -> i + i/8 */
+        const bool fused128 = (Ndft == 128);
+        F128Lane L128;
+        if (fused128) f128_init(L128, s_hann, lane);
+        const int mstride = fused128 ? F128_MSTRIDE : Ndft;
+        float2 *F = fftbuf + ew * (fused128 ? 4 * F128_STRIDE : PIPE_NFB * (Ndft + (Ndft >> 3)));       /* this warp's FFT buffers */
         unsigned par_pub = 0;
         PDECL
         for (int k = 0;; ++k) {
@@ -531,6 +563,29 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
             if (!(ck + nin_min <= nsamp_rel && (p.max_frames <= 0 || k < p.max_frames))) break;   /* frame k cannot exist */
             const float *Sf_in = Sfbuf + ((k + 1) & 1) * Ndft;
             float *Sf_out = Sfbuf + (k & 1) * Ndft;
+            if (fused128) {
+                /* Ndft = 128: four windows per round in two register passes (fsk_fft128.cuh).  A super-round = one round per EST warp
+                   (16 windows); their |X| rows go to magbuf, then the ordered Sf recursion runs over them (fsk.c:500) */
+                for (int r0 = 0; 4 * r0 < numffts; r0 += PIPE_NEST) {
+                    { PTIC
+                    if (4 * (r0 + ew) < numffts)
+                        est_round128<FMT, true>(p, gbase + ck, 4 * (r0 + ew), numffts, F, s_tw, L128, nullptr, nullptr, lane, magbuf - 4 * r0 * F128_MSTRIDE);
+                    PTOC(2); }
+                    { PTIC
+                    group_bar(1, NET);
+                    const int jend = min(numffts, 4 * (r0 + PIPE_NEST));
+                    const float *Sf_src = r0 ? Sf_out : Sf_in;
+                    for (int i = et; i < Ndft; i += NET) {
+                        float s = Sf_src[i];
+                        const int src = (i + Ndft / 2) & (Ndft - 1);
+                        for (int jj = 4 * r0; jj < jend; ++jj)
+                            s = __fadd_rn(__fmul_rn(s, p.omtc), __fmul_rn(magbuf[(jj - 4 * r0) * F128_MSTRIDE + src], p.tc));
+                        Sf_out[i] = s;
+                    }
+                    group_bar(1, NET);
+                    PTOC(3); }
+                }
+            } else
             /* this warp's windows: j = ew, ew+NEST, ... taken PIPE_NFB at a time so that the loads, butterflies and
                magnitudes of independent FFTs overlap (fsk.c:466-503) */
             for (int j0 = ew; j0 < numffts; j0 += PIPE_NEST * PIPE_NFB) {
@@ -572,14 +627,14 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
                 __syncwarp();
                 PTOC(2); }
             }
-            { PTIC
+            if (!fused128) { PTIC
             group_bar(1, NET);
             for (int i = et; i < Ndft; i += NET) {                       /* Sf IIR over the frame's FFTs, in order (fsk.c:500) */
                 float s = Sf_in[i];
                 const int src = (i + Ndft / 2) & (Ndft - 1);
 #pragma unroll 4
                 for (int jj = 0; jj < numffts; ++jj)
-                    s = __fadd_rn(__fmul_rn(s, p.omtc), __fmul_rn(magbuf[jj * Ndft + src], p.tc));
+                    s = __fadd_rn(__fmul_rn(s, p.omtc), __fmul_rn(magbuf[jj * mstride + src], p.tc));
                 Sf_out[i] = s;
             }
             group_bar(1, NET);
