@@ -76,6 +76,15 @@ int  b200dft_run_host(b200dft_t *h, const void *h_iq, int fmt, long in_stride, l
 int  b200dft_run_device(b200dft_t *h, const void *d_iq, int fmt, long in_stride, long nsamp, int opt_cont, double tl,
                         b200dft_result_t *res);
 
+/* ---- streaming form of the --iq mode: what ONE long-running dft_detect process does between reads, for nchan streams at once ----
+ * begin(fmt, -c, -t) resets the stream; every push appends nsamp samples per channel and advances the detector as far as the data
+ * allows.  res[nchan] must be the same array for the whole stream: new detections are APPENDED to res[c].dets (the caller may print
+ * them and reset res[c].ndet to 0 between pushes), res[c].exit_code is final once done[c] != 0 (first detection without -c, the -t
+ * limit, or flush != 0 = end of input).  Results are identical to one whole-buffer call over the concatenation of all pushes;
+ * the handle keeps only the K+L+... samples later blocks can still reach, so work and memory per push do not grow with the stream. */
+int  b200dft_stream_begin(b200dft_t *h, int fmt, int opt_cont, double tl);
+int  b200dft_stream_push_host(b200dft_t *h, const void *h_iq, long in_stride, long nsamp, int flush, b200dft_result_t *res, int *done);
+
 /* ---- wideband mode: `dft_detect --IQ <fq> --bw <kHz> [--dc] - <sr_base> <bits>` --------------------------------
  * The reference translates ONE candidate frequency per process out of a wide capture (rotation LUT + decimating low-pass,
  * dft_detect.c:751-761, tables :1021-1111; the same front as demod/mod/iq_dec.c:514-545) and then runs the detector at the

@@ -49,9 +49,48 @@ int main(int argc, char **argv)
         fprintf(stderr, "IF: %d\n", wb.if_sr); fprintf(stderr, "dec: %d\n", wb.decM);      /* :1067-1068 */
     }
     const int fmt = bits == 16 ? B200DFT_FMT_CS16 : (bits == 32 ? B200DFT_FMT_F32 : B200DFT_FMT_CU8), es = bits / 4;
+    b200dft_result_t res; memset(&res, 0, sizeof res);
+    if (!wide) {
+        /* --iq: streaming handle -- every read is pushed once, the library keeps the K+L samples later blocks still need (O(n) work,
+           constant memory, every detection printed: the reference's sample loop, dft_detect.c:1492-1652) */
+        const long step = sr / 4 > 4096 ? sr / 4 : 4096;
+        unsigned char *buf = malloc((size_t)step * es);
+        int done = 0, eof = 0;
+        if (b200dft_stream_begin(h, fmt, cont, tl) != B200DFT_OK) { fprintf(stderr, "dft_detect(b200): %s\n", b200dft_last_error()); return -50; }
+        while (!done) {
+            long n = 0;
+            for (;;) {                                     /* one read: a live pipe must not wait for a full buffer */
+                ssize_t r = read(0, buf, (size_t)step * es);
+                if (r < 0 && errno == EINTR) continue;
+                if (r <= 0) { eof = 1; break; }
+                long bytes = r;
+                while (bytes % es) { ssize_t r2 = read(0, buf + bytes, es - bytes % es); if (r2 <= 0) { eof = 1; bytes -= bytes % es; break; } bytes += r2; }
+                n = bytes / es;
+                break;
+            }
+            if (b200dft_stream_push_host(h, buf, n, n, eof, &res, &done) != B200DFT_OK) { fprintf(stderr, "dft_detect(b200): %s\n", b200dft_last_error()); return -50; }
+            for (int i = 0; i < res.ndet && i < B200DFT_MAXDET; i++) {                /* dft_detect.c:1620-1634 */
+                const b200dft_det_t *d = &res.dets[i];
+                if (silent) continue;
+                if (verbose) fprintf(stdout, "sample: %d\n", (int)d->pos);
+                fprintf(stdout, "%s: %.4f", d->type, d->score);
+                if ((!strncmp(d->type, "M10", 3) || !strncmp(d->type, "M20", 3)) && verbose) fprintf(stdout, " [%04X]", d->m10 & 0xFFFF);
+                if (dc) {
+                    fprintf(stdout, " , %+.1fHz", d->df_hz);
+                    if (verbose) { fprintf(stdout, "   [ fq-ofs: %+.6f", d->df_hz / sr); fprintf(stdout, " = %+.1fHz ]", d->df_hz); }
+                }
+                fprintf(stdout, "\n");
+            }
+            if (res.ndet > B200DFT_MAXDET) fprintf(stderr, "dft_detect(b200): %d detections in one read exceed the %d kept\n", res.ndet, B200DFT_MAXDET);
+            res.ndet = 0;
+            if (eof && !done) break;
+        }
+        free(buf);
+        b200dft_destroy(h);
+        return res.exit_code;
+    }
     long cap = (tl > 0 ? (long)((tl + 1) * sr) + 16 : (long)60 * sr), n = 0, step = sr / 2, next = step;
     unsigned char *buf = malloc((size_t)cap * es);
-    b200dft_result_t res; memset(&res, 0, sizeof res);
     int eof = 0, printed = 0;
     while (!eof) {
         while (n < next && n < cap) {

@@ -95,6 +95,7 @@ struct DftParams {
     BlkRes *res;                 /* [nz][nblk][nact] */
     const int *chan_list;        /* [nz] channel of grid.z entry (NULL: identity)                                   */
     const long long *sched_off;  /* [nz] samples consumed outside the block counter before this schedule (iMet branch) */
+    long long pos_base;          /* streaming: absolute index of sample 0 of the buffers (added to reported positions) */
 };
 
 /* raw sample -> float pair, the conversions of f32read_csample (dft_detect.c:561-578) */
@@ -408,7 +409,7 @@ __global__ void __launch_bounds__(CORR_THREADS, 2) dft_corr_kernel(const DftPara
             double t = 0; for (int w = 0; w < CORR_THREADS / 32; ++w) t += red[w];
             r.score = (float)((double)s_best / sqrt(t));
             const long long mpos = w0 + mp - taps / 2;                        /* :425,433 */
-            r.pos = (unsigned)mpos;
+            r.pos = (unsigned)(mpos + p.pos_base);
             if (r.score > h.thres || r.score < -h.thres) {                    /* candidate: headcmp (:866-901) */
                 unsigned char bits[96]; unsigned rc = 0; float gr = 0.0f;
                 const float hdc = p.opt_dc ? dc : 0.0f;
@@ -465,6 +466,20 @@ __global__ void dft_imet_kernel(const DftParams p, const ImetEv *ev, int m, int 
     if (threadIdx.x < 3) out[blockIdx.x * 3 + threadIdx.x] = pw[threadIdx.x];
 }
 
+/* Per-channel state of the decision loop of main() (dft_detect.c:1498-1652), resumable because the iMet AFSK branch
+ * (:1542-1607) swallows one extra second of samples OUTSIDE the block counter and so shifts every later block. */
+struct ChanRun {
+    float mv[NRS]; unsigned mv_pos[NRS], mv0_pos[NRS]; int mp[NRS]; float dcv[NRS], dfv[NRS];
+    const char *type[NRS]; int tn[NRS];
+    int j_max; float mv_max; unsigned frm2;
+    long long off;            /* samples consumed outside the block counter so far */
+    int b;                    /* next block of the current schedule */
+    bool done, need;
+    bool starved;             /* streaming: the next step needs samples that have not been pushed yet */
+    bool wait_imet; long long imet_ntrig; int imet_n, imet_hf;   /* an iMet candidate waits for its power test */
+    b200dft_result_t *out;
+};
+
 /* =============================== host side =================================================================== */
 struct b200dft {
     int sr, opt_dc, nchan, device; double bw_khz;
@@ -483,6 +498,11 @@ struct b200dft {
     float *d_ws_dec = 0; double *d_f0 = 0; float2 *d_wavg = 0; float2 *d_if = 0; void *d_wide = 0;
     long long cap_wavg = 0, cap_if = 0, cap_wide_bytes = 0;
     cudaEvent_t evc[2] = {0, 0}; bool ch_timed = false;
+    /* streaming (b200dft_stream_*): the tail of the raw input that later blocks still need, and the decision state of every channel */
+    bool st_active = false; int st_fmt = 0, st_cont = 0; double st_tl = -1.0;
+    long long st_abs0 = 0, st_have = 0, st_total = 0, st_cap = 0;
+    void *d_sbuf[2] = {0, 0}; int st_cur = 0;
+    std::vector<ChanRun> st_run; b200dft_result_t *st_res = 0;
 };
 
 static double sinc_(double x) { return x == 0 ? 1 : sin(M_PI * x) / (M_PI * x); }
@@ -591,7 +611,7 @@ extern "C" void b200dft_destroy(b200dft_t *h)
 {
     if (!h) return;
     cudaSetDevice(h->device); cudaDeviceSynchronize();
-    void *ptrs[] = {h->d_ws_lpIQ, h->d_ws_lpFM, h->d_match, h->d_hdr, h->d_avg, h->d_fm_filt, h->d_fm_raw, h->d_res, h->d_iq, h->d_list, h->d_soff,
+    void *ptrs[] = {h->d_ws_lpIQ, h->d_ws_lpFM, h->d_match, h->d_hdr, h->d_avg, h->d_fm_filt, h->d_fm_raw, h->d_res, h->d_iq, h->d_list, h->d_soff, h->d_sbuf[0], h->d_sbuf[1],
                     h->d_ws_dec, h->d_f0, h->d_wavg, h->d_if, h->d_wide};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < 4; i++) cudaEventDestroy(h->ev[i]);
@@ -607,19 +627,6 @@ extern "C" int b200dft_info(const b200dft_t *h, b200dft_info_t *info)
     info->lpIQtaps = h->lpIQtaps; info->lpFMtaps = h->lpFMtaps; info->nhdr_active = h->nact; info->nchan = h->nchan;
     return B200DFT_OK;
 }
-
-/* Per-channel state of the decision loop of main() (dft_detect.c:1498-1652), resumable because the iMet AFSK branch
- * (:1542-1607) swallows one extra second of samples OUTSIDE the block counter and so shifts every later block. */
-struct ChanRun {
-    float mv[NRS]; unsigned mv_pos[NRS], mv0_pos[NRS]; int mp[NRS]; float dcv[NRS], dfv[NRS];
-    const char *type[NRS]; int tn[NRS];
-    int j_max; float mv_max; unsigned frm2;
-    long long off;            /* samples consumed outside the block counter so far */
-    int b;                    /* next block of the current schedule */
-    bool done, need;
-    bool wait_imet; long long imet_ntrig; int imet_n, imet_hf;   /* an iMet candidate waits for its power test */
-    b200dft_result_t *out;
-};
 
 static void chan_init(ChanRun &s, b200dft_result_t *out)
 {
@@ -674,15 +681,26 @@ static void chan_resume_imet(b200dft *h, ChanRun &s, int verdict, int opt_cont)
 
 /* Advance one channel over the results of its current schedule; stops at the end of the stream, at the first detection
  * (no -c), when the schedule's results run out, or at an iMet candidate (s.wait_imet: the caller runs the power test). */
-static void chan_advance(b200dft *h, ChanRun &s, const BlkRes *res, int nblk_launch, long neff, int opt_cont)
+static void chan_advance(b200dft *h, ChanRun &s, const BlkRes *res, int nblk_launch, long long neff, int opt_cont, bool final = true)
 {
     const int nact = h->nact, Kb = h->K - 4;
     s.need = false;
     while (!s.done && !s.need && !s.wait_imet) {
         const long long n_trig = s.off + (long long)(s.b + 1) * Kb;
-        if (n_trig > neff) { chan_finish(s); return; }
+        if (n_trig > neff) { if (final) chan_finish(s); else s.starved = true; return; }
         if (s.b >= nblk_launch) { s.need = true; return; }
         const BlkRes *rb = res + (size_t)s.b * nact;
+        if (!final && neff - n_trig < h->sr) {
+            /* streaming: an iMet AFSK candidate in this block would read one more second of samples (:1542-1607) that has not arrived
+               yet -- look before touching any state, and wait for the next push if so */
+            for (int a = 0; a < nact; a++) {
+                const int j = h->act[a];
+                if (j != IDX_IMETAFSK) continue;
+                const float mvj = rb[a].mp > 0 ? rb[a].score : s.mv[j];
+                const unsigned pj = rb[a].mp > 0 ? rb[a].pos : s.mv_pos[j];
+                if (rb[a].mp > 0 && (mvj > HDR[j].thres || mvj < -HDR[j].thres) && pj > s.mv_pos[j] && rb[a].herrs < HDR[j].herrs) { s.starved = true; return; }
+            }
+        }
         for (int a = 0; a < nact; a++) {
             const int j = h->act[a];
             s.mv0_pos[j] = s.mv_pos[j];
@@ -819,6 +837,179 @@ static int run_common(b200dft *h, const void *d_iq, int fmt, long in_stride, lon
         CK(cudaStreamSynchronize(s));
         rbase = r2.data(); nb_cur = nb2; identity = false;
     }
+    return B200DFT_OK;
+}
+
+/* ---- streaming form (ADVICE r01 / VERDICT r01 #4): the handle keeps what the reference process keeps between reads ---------------------
+ * The reference is a sample loop with all state in statics: DC-block sums, FIR ring, previous IF sample, FM rings, block counter,
+ * mv/mv_pos per header.  Every one of them depends on a BOUNDED past: the FM value of sample n needs the raw samples of the previous
+ * DC block and lpIQtaps more, a correlation block needs K+L+delay+lpFMtaps FM samples.  So the handle keeps the raw tail that the next
+ * undecided block of any channel can still reach (rounded down to a DC-block boundary minus one block, so the kernels recompute exactly
+ * the reference's values for everything they are asked about) plus the per-channel decision state (ChanRun), and every push runs the
+ * same kernels as the whole-buffer call over [tail + new samples] with absolute positions.  Work per push is O(new samples + K+L). */
+extern "C" int b200dft_stream_begin(b200dft_t *h, int fmt, int opt_cont, double tl)
+{
+    if (!h) return fail(B200DFT_EINVAL, "null");
+    if (h->wide) return fail(B200DFT_EINVAL, "streaming is implemented for the --iq mode");
+    if (fmt < 0 || fmt > 2) return fail(B200DFT_ERANGE, "fmt");
+    h->st_active = true; h->st_fmt = fmt; h->st_cont = opt_cont ? 1 : 0; h->st_tl = tl;
+    h->st_abs0 = h->st_have = h->st_total = 0; h->st_res = 0;
+    h->st_run.assign(h->nchan, ChanRun());
+    return B200DFT_OK;
+}
+
+static int stream_step(b200dft *h, bool final)
+{
+    const int Kb = h->K - 4, nact = h->nact;
+    const long long neff = h->st_have, neff_abs = h->st_abs0 + neff;
+    std::vector<int> todo;
+    for (int c = 0; c < h->nchan; c++) {
+        ChanRun &s = h->st_run[c];
+        if (s.done) continue;
+        s.off += (long long)s.b * Kb; s.b = 0; s.starved = false; s.need = false;      /* the schedule restarts at the next undecided block */
+        todo.push_back(c);
+    }
+    if (todo.empty()) return B200DFT_OK;
+    int nbmax = 0;
+    for (int c : todo) { const long long nb = (neff_abs - h->st_run[c].off) / Kb; if (nb > nbmax) nbmax = (int)nb; }
+    if (nbmax <= 0) { if (final) for (int c : todo) chan_finish(h->st_run[c]); return B200DFT_OK; }
+    const int navg = (int)(neff / h->maxcnt) + 2;
+    if (neff > h->cap_samp) {
+        if (h->d_fm_filt) cudaFree(h->d_fm_filt); if (h->d_fm_raw) cudaFree(h->d_fm_raw);
+        const long long cap = neff + neff / 2;
+        CK(cudaMalloc(&h->d_fm_filt, (size_t)h->nchan * cap * 4)); CK(cudaMalloc(&h->d_fm_raw, (size_t)h->nchan * cap * 4));
+        h->cap_samp = cap;
+    }
+    h->cap_samp_run = neff;
+    if (navg > h->cap_avg) { if (h->d_avg) cudaFree(h->d_avg); CK(cudaMalloc(&h->d_avg, (size_t)h->nchan * navg * sizeof(float2))); h->cap_avg = navg; }
+    if (nbmax > h->cap_blk) { if (h->d_res) cudaFree(h->d_res); CK(cudaMalloc(&h->d_res, (size_t)h->nchan * nbmax * nact * sizeof(BlkRes))); h->cap_blk = nbmax; }
+    if (!h->d_list) { CK(cudaMalloc(&h->d_list, sizeof(int) * h->nchan)); CK(cudaMalloc(&h->d_soff, sizeof(long long) * h->nchan)); }
+    DftParams p; memset(&p, 0, sizeof p);
+    p.nchan = h->nchan; p.nact = nact; p.N = h->N; p.K = h->K; p.L = h->L; p.lpIQtaps = h->lpIQtaps; p.lpFMtaps = h->lpFMtaps; p.tpad = (h->lpFMtaps + CORR_R - 1) / CORR_R * CORR_R;
+    p.delay = h->delay; p.opt_dc = h->opt_dc; p.maxcnt = h->maxcnt; p.nblk = nbmax; p.navg = navg; p.nsamp = neff; p.in_stride = h->st_cap;
+    p.fmt = h->st_fmt; p.iq = h->d_sbuf[h->st_cur]; p.ws_lpIQ = h->d_ws_lpIQ; p.ws_lpFM = h->d_ws_lpFM; p.match = h->d_match; p.hdr = h->d_hdr;
+    p.avg = h->d_avg; p.fm_filt = h->d_fm_filt; p.fm_raw = h->d_fm_raw; p.res = h->d_res; p.pos_base = h->st_abs0;
+    cudaStream_t s = h->stream;
+    CK(cudaEventRecord(h->ev[0], s));
+    {
+        dim3 g0((unsigned)(navg - 1), h->nchan);
+        dft_dcavg_kernel<<<g0, 128, 0, s>>>(p);
+        dim3 g1((unsigned)((neff + FRONT_TILE - 1) / FRONT_TILE), h->nchan);
+        dft_front_kernel<<<g1, FRONT_TILE, (size_t)(2 * FRONT_TILE + h->lpIQtaps + 1) * sizeof(float2), s>>>(p);
+        h->launches += 2;
+    }
+    CK(cudaEventRecord(h->ev[1], s));
+    const float dfb = (1 / (float)h->N) * h->sr;
+    int m_imet = 50.0 / dfb; if (m_imet < 1) m_imet = 1;
+    const bool imet_ok = !(2500 * h->N / (float)h->sr > h->N / 2);
+    std::vector<BlkRes> r2;
+    while (!todo.empty()) {
+        const int nz = (int)todo.size();
+        std::vector<long long> off(nz); int nb2 = 0;
+        for (int z = 0; z < nz; z++) {
+            const ChanRun &st = h->st_run[todo[z]];
+            off[z] = st.off - h->st_abs0;
+            const int nb = (int)((neff_abs - st.off) / Kb); if (nb > nb2) nb2 = nb;
+        }
+        if (nb2 > 0) {
+            if ((long long)nz * nb2 > (long long)h->nchan * h->cap_blk) return fail(B200DFT_ERANGE, "relaunch buffer");
+            CK(cudaMemcpyAsync(h->d_list, todo.data(), sizeof(int) * nz, cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(h->d_soff, off.data(), sizeof(long long) * nz, cudaMemcpyHostToDevice, s));
+            DftParams q = p; q.nblk = nb2; q.chan_list = h->d_list; q.sched_off = h->d_soff;
+            dim3 g2(nb2, nact, nz);
+            dft_corr_kernel<<<g2, CORR_THREADS, h->corr_smem_max, s>>>(q);
+            h->launches += 1;
+            CK(cudaGetLastError());
+            r2.resize((size_t)nz * nb2 * nact);
+            CK(cudaMemcpyAsync(r2.data(), h->d_res, r2.size() * sizeof(BlkRes), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+        }
+        std::vector<int> pend;
+        for (int z = 0; z < nz; z++) {
+            ChanRun &st = h->st_run[todo[z]];
+            chan_advance(h, st, r2.data() + (size_t)z * nb2 * nact, nb2, neff_abs, h->st_cont, final);
+            if (st.wait_imet) pend.push_back(todo[z]);
+        }
+        if (!pend.empty()) {
+            const int ne = (int)pend.size();
+            std::vector<ImetEv> ev(ne); std::vector<float> pw(3 * ne);
+            for (int i = 0; i < ne; i++) { const ChanRun &st = h->st_run[pend[i]]; ev[i].c = pend[i]; ev[i].n = st.imet_n; ev[i].src = st.imet_ntrig - h->delay - h->st_abs0; }
+            ImetEv *d_ev = 0; float *d_pw = 0;
+            CK(cudaMalloc(&d_ev, sizeof(ImetEv) * ne)); CK(cudaMalloc(&d_pw, sizeof(float) * 3 * ne));
+            CK(cudaMemcpy(d_ev, ev.data(), sizeof(ImetEv) * ne, cudaMemcpyHostToDevice));
+            dft_imet_kernel<<<ne, 256, 0, s>>>(p, d_ev, m_imet, (int)(2200 * h->N / (float)h->sr), (int)(2400 * h->N / (float)h->sr), (int)(800 * h->N / (float)h->sr), d_pw);
+            h->launches += 1;
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(pw.data(), d_pw, sizeof(float) * 3 * ne, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            cudaFree(d_ev); cudaFree(d_pw);
+            for (int i = 0; i < ne; i++) {
+                const int verdict = !imet_ok ? -1 : ((pw[3 * i] > pw[3 * i + 1] && pw[3 * i] > pw[3 * i + 2]) ? 1 : 0);
+                chan_resume_imet(h, h->st_run[pend[i]], verdict, h->st_cont);
+            }
+        }
+        std::vector<int> next;
+        for (int z = 0; z < nz; z++) { const ChanRun &st = h->st_run[todo[z]]; if (!st.done && st.need && !st.starved) next.push_back(todo[z]); }
+        todo.swap(next);
+    }
+    CK(cudaEventRecord(h->ev[2], s));
+    h->timed = true;
+    return B200DFT_OK;
+}
+
+extern "C" int b200dft_stream_push_host(b200dft_t *h, const void *h_iq, long in_stride, long nsamp, int flush, b200dft_result_t *res, int *done)
+{
+    if (!h || !res || (nsamp > 0 && !h_iq)) return fail(B200DFT_EINVAL, "null");
+    if (!h->st_active) return fail(B200DFT_EINVAL, "b200dft_stream_begin first");
+    if (nsamp < 0) return fail(B200DFT_ERANGE, "nsamp");
+    CK(cudaSetDevice(h->device));
+    if (!h->st_res) { h->st_res = res; for (int c = 0; c < h->nchan; c++) chan_init(h->st_run[c], &res[c]); }
+    else if (h->st_res != res) return fail(B200DFT_EINVAL, "the result array must stay the same for the whole stream");
+    const int es = h->st_fmt == 1 ? 8 : (h->st_fmt == 0 ? 4 : 2);
+    long long lim = -1;                                  /* -t: the reference stops reading at (tl+1)*sr samples (:1494) */
+    if (h->st_tl > 0) lim = (long long)floor((h->st_tl + 1) * h->sr);
+    long long acc = nsamp;
+    if (lim >= 0 && h->st_total + acc > lim) acc = lim > h->st_total ? lim - h->st_total : 0;
+    const bool final = flush || (lim >= 0 && h->st_total + acc >= lim);
+    if (h->st_have + acc > h->st_cap) {                  /* grow both buffers, keep the tail */
+        const long long ncap = (h->st_have + acc) * 2 + 4096;
+        void *nb[2] = {0, 0};
+        CK(cudaMalloc(&nb[0], (size_t)h->nchan * ncap * es)); CK(cudaMalloc(&nb[1], (size_t)h->nchan * ncap * es));
+        CK(cudaStreamSynchronize(h->stream));
+        if (h->st_have > 0)
+            CK(cudaMemcpy2D(nb[0], (size_t)ncap * es, h->d_sbuf[h->st_cur], (size_t)h->st_cap * es, (size_t)h->st_have * es, h->nchan, cudaMemcpyDeviceToDevice));
+        for (int i = 0; i < 2; i++) { if (h->d_sbuf[i]) cudaFree(h->d_sbuf[i]); h->d_sbuf[i] = nb[i]; }
+        h->st_cap = ncap; h->st_cur = 0;
+    }
+    if (acc > 0)
+        CK(cudaMemcpy2DAsync((char *)h->d_sbuf[h->st_cur] + (size_t)h->st_have * es, (size_t)h->st_cap * es, h_iq, (size_t)in_stride * es, (size_t)acc * es,
+                             h->nchan, cudaMemcpyHostToDevice, h->stream));
+    h->st_have += acc; h->st_total += acc;
+    const int rc = stream_step(h, final);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    /* drop what no later block can reach */
+    long long keep = -1;
+    for (int c = 0; c < h->nchan; c++) {
+        const ChanRun &st = h->st_run[c];
+        if (st.done) continue;
+        const long long n_trig = st.off + (long long)(st.b + 1) * (h->K - 4);
+        const long long w0 = n_trig - 1 - h->delay - (h->K + h->L - 1) - (h->lpFMtaps + 2 * CORR_R + 16);
+        const long long from = w0 - h->lpIQtaps - h->maxcnt - 8;
+        if (keep < 0 || from < keep) keep = from;
+    }
+    if (keep > h->st_abs0) {
+        const long long nabs = keep / h->maxcnt * h->maxcnt;
+        const long long shift = nabs - h->st_abs0;
+        if (shift > 0 && shift <= h->st_have) {
+            const long long rest = h->st_have - shift;
+            if (rest > 0)
+                CK(cudaMemcpy2DAsync(h->d_sbuf[h->st_cur ^ 1], (size_t)h->st_cap * es, (char *)h->d_sbuf[h->st_cur] + (size_t)shift * es, (size_t)h->st_cap * es,
+                                     (size_t)rest * es, h->nchan, cudaMemcpyDeviceToDevice, h->stream));
+            h->st_cur ^= 1; h->st_have = rest; h->st_abs0 = nabs;
+        }
+    }
+    if (done) for (int c = 0; c < h->nchan; c++) done[c] = h->st_run[c].done ? 1 : 0;
     return B200DFT_OK;
 }
 

@@ -66,6 +66,8 @@ def lib() -> C.CDLL:
         L.b200dft_last_error.restype = C.c_char_p
         L.b200dft_run_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_long, C.c_long, C.c_int, C.c_double, C.c_void_p]
         L.b200dft_run_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_long, C.c_long, C.c_int, C.c_double, C.c_void_p]
+        L.b200dft_stream_begin.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
+        L.b200dft_stream_push_host.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_long, C.c_int, C.c_void_p, C.c_void_p]
         L.b200dft_launch_count.argtypes = [C.c_void_p]
         L.b200dft_launch_count.restype = C.c_long
         L.b200dft_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
@@ -131,6 +133,29 @@ class DftDetectBatch:
         ptr = d_iq.data_ptr() if hasattr(d_iq, "data_ptr") else int(d_iq)
         _ck(self.L.b200dft_run_device(self.h, C.c_void_p(ptr), f, in_stride or nsamp, nsamp, int(cont), float(tl), res))
         return self._collect(res)
+
+    # ---- streaming form: what one long-running dft_detect process does between reads (include/b200dft.h) ----
+    def stream_begin(self, fmt: str = "cs16", cont: bool = False, tl: float = -1.0) -> None:
+        self._sres = (_Res * self.nchan)()
+        self._sdone = (C.c_int * self.nchan)()
+        self._sdets = [[] for _ in range(self.nchan)]
+        self._sfmt = fmt
+        _ck(self.L.b200dft_stream_begin(self.h, {"cs16": 0, "f32": 1, "cu8": 2}[fmt], int(cont), float(tl)))
+
+    def stream_push(self, iq: np.ndarray, flush: bool = False):
+        """append iq [nchan, n, 2] to the streams -> [(exit_code or None while running, all detections so far)] per channel"""
+        iq = np.ascontiguousarray(iq).reshape(self.nchan, -1)
+        n = iq.shape[1] // 2
+        _ck(self.L.b200dft_stream_push_host(self.h, iq.ctypes.data if n else None, n, n, int(flush), self._sres, self._sdone))
+        out = []
+        for c in range(self.nchan):
+            r = self._sres[c]
+            assert r.ndet <= 64, "more than B200DFT_MAXDET detections in one push"
+            self._sdets[c] += [Detection(r.dets[i].type.decode(), r.dets[i].score, r.dets[i].pos, r.dets[i].df_hz, r.dets[i].tn, r.dets[i].m10)
+                               for i in range(r.ndet)]
+            r.ndet = 0                                    # printed: the library appends the next ones from slot 0
+            out.append((r.exit_code if self._sdone[c] else None, list(self._sdets[c])))
+        return out
 
     def kernel_ms(self):
         a, b = C.c_float(0), C.c_float(0)

@@ -32,6 +32,17 @@ FSK_CASES = {
 DFT_CASES = {k: dict(seed=700 + i, kind=k, nsamp=60000, snr_db=16.0) for i, k in enumerate(["RS41", "DFM9", "M10", "MTS01", "WXR301", "noise"])}
 
 
+# 96 kHz IF (auto_rx wideband_sondes: `dft_detect ... --iq --bw 64 --dc - 96000 16`, scan.py:476-482; everything in the detector doubles:
+# N_DFT 16384, K 11264, FIR taps 97/193): name -> (kind, --bw kHz, FM deviation Hz, seed)
+DFT96_CASES = {"WXR301_bw64": ("WXR301", 64.0, 12000.0, 801), "WXRPN9_bw64": ("WXRPN9", 64.0, 12000.0, 802), "RS41_bw32": ("RS41", 32.0, 2400.0, 803),
+               "DFM9_bw64": ("DFM9", 64.0, 2400.0, 804), "noise_bw64": ("noise", 64.0, 0.0, 805)}
+
+
+def dft96_input(name):
+    kind, _, dev, seed = DFT96_CASES[name]
+    return siggen.noise_iq(seed, 240000) if kind == "noise" else siggen.fm_header_iq(seed, 240000, kind, Fs=96000, dev_hz=dev, snr_db=17.0)
+
+
 def fsk_input(name):
     ck, sk, n = FSK_CASES[name]
     if sk is None:
@@ -86,6 +97,12 @@ def main():
         rc, dets = po.ref_cli_dft_detect(iq, 48000, 15.0, True, True)
         dj[name] = {"exit_code": rc, "dets": dets, "sha": hashlib.sha256(iq.tobytes()).hexdigest()}
     json.dump(dj, open(os.path.join(HERE, "golden_dft.json"), "w"), indent=1)
+    d96 = {}
+    for name, (kind, bw, _, _) in DFT96_CASES.items():
+        iq = dft96_input(name)
+        rc, dets = po.ref_cli_dft_detect(iq, 96000, bw, True, True)      # dft_detect -v -c --iq --bw <bw> --dc - 96000 16
+        d96[name] = {"exit_code": rc, "dets": dets, "bw": bw, "sha": hashlib.sha256(iq.tobytes()).hexdigest()}
+    json.dump(d96, open(os.path.join(HERE, "golden_dft96.json"), "w"), indent=1)
     wj = {}
     for name, (sr, _, _, _, hz) in DFT_WB_CASES.items():
         iq = dft_wb_input(name)
@@ -106,7 +123,7 @@ def main():
             ent[f"ecc{ecc}"] = [[hashlib.sha1(h.encode()).hexdigest()[:16], t.strip()] for h, t in ref]
         rj[str(seed)] = ent
     json.dump(rj, open(os.path.join(HERE, "golden_rs41.json"), "w"), indent=1)
-    print("wrote golden_fsk.npz, golden_dft.json, golden_dft_wb.json, golden_rs41.json")
+    print("wrote golden_fsk.npz, golden_dft.json, golden_dft96.json, golden_dft_wb.json, golden_rs41.json")
 
 
 if __name__ == "__main__":

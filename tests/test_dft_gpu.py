@@ -75,6 +75,40 @@ def test_no_dc_and_other_bandwidth(cuda):
             compare(got[c], rc, dets, f"{k} bw={bw} dc={dc}")
 
 
+@pytest.mark.parametrize("sr,bw,cont,tl", [(48000, 15.0, True, -1.0), (48000, 15.0, False, -1.0), (96000, 64.0, True, -1.0), (48000, 15.0, True, 2.0)])
+def test_streaming_pushes_equal_whole_buffer(cuda, sr, bw, cont, tl):
+    """b200dft_stream_*: arbitrary chunking of the input (1 sample .. several blocks per push) gives the detections, positions and exit
+    codes of one whole-buffer run -- including channels whose iMet AFSK branch shifts the block schedule -- while the handle only keeps
+    the tail later blocks can reach."""
+    nsamp = 300_000 if sr == 48000 else 400_000
+    kinds = ["RS41", "DFM9", "MRZ", "noise", "MEISEI", "M10"] if sr == 48000 else ["WXR301", "RS41", "noise", "DFM9"]
+    chans = []
+    for i, k in enumerate(kinds):
+        if k == "noise":
+            chans.append(siggen.noise_iq(40 + i, nsamp))
+        else:
+            chans.append(siggen.fm_header_iq(9000 + i, nsamp, k, Fs=sr, dev_hz=12000.0 if k.startswith("WXR") else 2400.0, snr_db=14.0, invert=(i == 2)))
+    iq = np.stack(chans)
+    b = dft.DftDetectBatch(sr, bw, True, nchan=len(kinds))
+    whole = b.run(iq, cont=cont, tl=tl)
+    b.stream_begin("cs16", cont=cont, tl=tl)
+    rng = np.random.default_rng(7)
+    pos, got = 0, None
+    while pos < nsamp:
+        n = int(min(nsamp - pos, rng.choice([1, 37, 1500, 4000, 11000, 30000])))
+        got = b.stream_push(iq[:, pos:pos + n])
+        pos += n
+    got = b.stream_push(iq[:, :0], flush=True)
+    for c, k in enumerate(kinds):
+        rc, dets = whole[c]
+        assert got[c][0] == rc, (k, got[c][0], rc)
+        g = got[c][1][:len(dets)]          # the whole-buffer call keeps at most B200DFT_MAXDET detections, the stream reports all
+        assert len(got[c][1]) >= len(dets) and [(d.type, d.pos) for d in g] == [(d.type, d.pos) for d in dets], k
+        for a, e in zip(g, dets):
+            assert abs(a.score - e.score) < 1e-6 and abs(a.df_hz - e.df_hz) < 1e-3
+    assert sum(len(g[1]) for g in got) >= 3
+
+
 def test_output_text_matches_reference_format(cuda):
     iq, _ = build_channels(60_000, ["RS41"], seed=900)
     b = dft.DftDetectBatch(48000, 15.0, True, nchan=1)

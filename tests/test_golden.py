@@ -16,6 +16,7 @@ from oracle import pyoracle as po                      # noqa: E402
 G = np.load(os.path.join(HERE, "golden_fsk.npz"))
 GD = json.load(open(os.path.join(HERE, "golden_dft.json")))
 GW = json.load(open(os.path.join(HERE, "golden_dft_wb.json")))
+G96 = json.load(open(os.path.join(HERE, "golden_dft96.json")))
 
 
 @pytest.mark.parametrize("name", list(mg.FSK_CASES))
@@ -39,6 +40,38 @@ def test_dft_oracle_reproduces_golden(built, name):
     assert rc == GD[name]["exit_code"] and len(dets) == len(GD[name]["dets"])
     for a, b in zip(dets, GD[name]["dets"]):
         assert a[0] == b[0] and a[2] == b[2] and abs(a[1] - b[1]) < 1e-3 and abs(a[3] - b[3]) < 0.2
+
+
+@pytest.mark.parametrize("name", list(mg.DFT96_CASES))
+def test_dft_96khz_oracle_reproduces_golden(built, name):
+    """the 96 kHz IF of auto_rx's wideband sondes (scan.py:476-482): N_DFT 16384, 97/193 taps"""
+    iq = mg.dft96_input(name)
+    g = G96[name]
+    assert hashlib.sha256(iq.tobytes()).hexdigest() == g["sha"]
+    rc, dets, _ = po.dft_oracle_run(iq, 96000, g["bw"], True, True)
+    assert rc == g["exit_code"] and len(dets) == len(g["dets"])
+    for a, b in zip(dets, g["dets"]):
+        assert a[0] == b[0] and a[2] == b[2] and abs(a[1] - b[1]) < 1e-3 and abs(a[3] - b[3]) < 0.2
+
+
+@pytest.mark.gpu
+def test_dft_96khz_cuda_reproduces_golden(cuda):
+    """`dft_detect -c -v --iq --bw {64|32} --dc - 96000 16` on the GPU against the reference binary's recorded output"""
+    from radiosonde_auto_rx_b200 import dft
+    ndet = 0
+    for bw in sorted({g["bw"] for g in G96.values()}):
+        names = [n for n in mg.DFT96_CASES if G96[n]["bw"] == bw]
+        iq = np.stack([mg.dft96_input(n) for n in names])
+        b = dft.DftDetectBatch(96000, bw, True, nchan=len(names))
+        assert b.N_DFT == 16384
+        got = b.run(iq, cont=True)
+        for (rc, dets), n in zip(got, names):
+            g = G96[n]
+            assert rc == g["exit_code"] and len(dets) == len(g["dets"]), (n, rc, dets, g)
+            for d, e in zip(dets, g["dets"]):
+                assert d.type == e[0] and d.pos == e[2] and abs(d.score - e[1]) < 2e-4 and abs(d.df_hz - e[3]) < 0.2
+            ndet += len(dets)
+    assert ndet >= 8
 
 
 @pytest.mark.parametrize("name", list(mg.DFT_WB_CASES))
