@@ -40,6 +40,7 @@ struct b200fsk {
     size_t smem_pipe = 0; bool use_pipe = false;   /* pipelined kernel */
     size_t smem_wpc = 0; bool can_wpc = false, force_wpc = false; int wpc_G = 0, nsm = 0;   /* throughput kernel (many channels per CTA) */
     float2 *d_fint = 0; int *d_abort = 0; int wpc_thresh = 1 << 30;
+    float2 *d_gring = 0;
     unsigned short *d_invperm = 0;
     std::vector<float> h_fest;         /* LUT: tone estimate in Hz per table index */
     /* device tables */
@@ -95,12 +96,14 @@ static int plan_fft(int n, FskKParams &kp, std::vector<unsigned short> &perm)
 
 /* the pipelined kernel is specialised on tone count and input sample format */
 typedef void (*pipe_fn_t)(const FskKParams);
-static const void *pipe_kernel_fn(int M, int fmt)
+static const void *pipe_kernel_fn(int M, int fmt, int oscp = 0)
 {
-    static const pipe_fn_t tab[2][4] = {
-        {fsk_demod_pipe_kernel<2, 0>, fsk_demod_pipe_kernel<2, 1>, fsk_demod_pipe_kernel<2, 2>, fsk_demod_pipe_kernel<2, 3>},
-        {fsk_demod_pipe_kernel<4, 0>, fsk_demod_pipe_kernel<4, 1>, fsk_demod_pipe_kernel<4, 2>, fsk_demod_pipe_kernel<4, 3>}};
-    return (const void *)tab[M == 4 ? 1 : 0][fmt & 3];
+    static const pipe_fn_t tab[2][2][4] = {
+        {{fsk_demod_pipe_kernel<2, 0, false>, fsk_demod_pipe_kernel<2, 1, false>, fsk_demod_pipe_kernel<2, 2, false>, fsk_demod_pipe_kernel<2, 3, false>},
+         {fsk_demod_pipe_kernel<4, 0, false>, fsk_demod_pipe_kernel<4, 1, false>, fsk_demod_pipe_kernel<4, 2, false>, fsk_demod_pipe_kernel<4, 3, false>}},
+        {{fsk_demod_pipe_kernel<2, 0, true>, fsk_demod_pipe_kernel<2, 1, true>, fsk_demod_pipe_kernel<2, 2, true>, fsk_demod_pipe_kernel<2, 3, true>},
+         {fsk_demod_pipe_kernel<4, 0, true>, fsk_demod_pipe_kernel<4, 1, true>, fsk_demod_pipe_kernel<4, 2, true>, fsk_demod_pipe_kernel<4, 3, true>}}};
+    return (const void *)tab[oscp ? 1 : 0][M == 4 ? 1 : 0][fmt & 3];
 }
 
 static const void *wpc_kernel_fn(int M, int fmt)
@@ -238,7 +241,7 @@ extern "C" int b200fsk_create(b200fsk_t **out, const b200fsk_cfg_t *cfg, int nch
         const int f0 = (int)floor((float)nmin / (Ndft / 2)), f1 = (int)floor((float)nmax / (Ndft / 2));
         size_t q = 0;
         auto takeq = [&](size_t bytes) { size_t r = q; q += (bytes + 15) & ~(size_t)15; return (int)r; };
-        kp.q_ring = takeq((size_t)M * PIPE_R * 8); kp.q_fint = takeq((size_t)2 * M * nfi * 8); kp.q_stage_bytes = 2 * M * nfi * 8;
+        kp.q_ring = takeq((size_t)M * PIPE_RS * 8); kp.q_fint = takeq((size_t)2 * M * nfi * 8); kp.q_stage_bytes = 2 * M * nfi * 8;
         kp.q_fft = takeq((size_t)PIPE_NEST * (Ndft == 128 ? 4 * F128_STRIDE : PIPE_NFB * (Ndft + Ndft / 8)) * 8);
         kp.q_mag = takeq(Ndft == 128 ? (size_t)4 * PIPE_NEST * F128_MSTRIDE * 4 : (size_t)(f0 > 1 ? f0 - 1 : 1) * Ndft * 4);
         kp.q_Sf = takeq((size_t)2 * Ndft * 4); kp.q_hann = takeq(Ndft * 4); kp.q_tw = takeq(Ndft * 8); kp.q_perm = takeq(Ndft * 2);
@@ -291,7 +294,7 @@ extern "C" int b200fsk_create(b200fsk_t **out, const b200fsk_cfg_t *cfg, int nch
         if (G > WPC_MAXG) G = WPC_MAXG;
         kp.w_ring = ring; kp.w_blk = blk; kp.w_chan_stride = (int)stride;
         h->wpc_G = G;
-        h->wpc_thresh = 2 * h->nsm;                               /* above two channels per SM the throughput kernel takes over */
+        h->wpc_thresh = 4 * h->nsm - 1;                           /* measured cross-over (profiles/r02_notes.md): from 4 channels per SM the throughput kernel wins */
         if (const char *t = getenv("B200FSK_WPC_THRESH")) h->wpc_thresh = atoi(t);
         h->can_wpc = (f0 == f1) && (f0 - 1 >= 1) && (3 * Ts + 2 * blk + 16 <= ring) && (nfi >= 2) && (Ndft <= 256) && G >= 1;
         const char *force = getenv("B200FSK_KERNEL");
@@ -306,10 +309,11 @@ extern "C" int b200fsk_create(b200fsk_t **out, const b200fsk_cfg_t *cfg, int nch
     CKH(allow_max_smem((const void *)fsk_demod_kernel, maxsmem));
     if (h->use_pipe) {
         for (int f = 0; f < 4; ++f) {
-            const void *fn = pipe_kernel_fn(M, f);
-            CKH(allow_max_smem(fn, maxsmem));
+            CKH(allow_max_smem(pipe_kernel_fn(M, f, 0), maxsmem));
+            CKH(allow_max_smem(pipe_kernel_fn(M, f, 1), maxsmem));
         }
     }
+    if (h->use_pipe) { CKH(zalloc(&h->d_gring, (size_t)nchan * M * PIPE_R)); kp.g_ring = h->d_gring; }
     if (h->can_wpc) {
         for (int f = 0; f < 4; ++f) CKH(allow_max_smem(wpc_kernel_fn(M, f), maxsmem));
         {   /* f_int spill: one slot per (SM, channel warp); with WPC_CTAS > 1 two CTAs may share an SM -> fall back to per-channel slots */
@@ -358,7 +362,7 @@ extern "C" void b200fsk_destroy(b200fsk_t *h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->d_invperm, h->d_hann, h->d_tw, h->d_perm, h->d_phi_ft, h->d_mask, h->d_dphi, h->d_Sf, h->d_phi, h->d_tail, h->d_nrt,
                     h->d_ppm, h->d_nin, h->d_last, h->d_totf, h->d_tots, h->d_nframes, h->d_consumed, h->d_eye, h->d_recs,
-                    h->d_stage[0], h->d_stage[1], h->d_off, h->d_out, h->d_fbase, h->d_fint, h->d_abort};
+                    h->d_stage[0], h->d_stage[1], h->d_off, h->d_out, h->d_fbase, h->d_fint, h->d_abort, h->d_gring};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -456,8 +460,12 @@ static int launch(b200fsk *h, FskKParams &kp, cudaStream_t s, bool time_it)
         h->last_kind = 2;
     } else if (h->use_pipe) {
         h->last_kind = 1;
+        /* one CTA per SM: the oscillator's stores are worth software-pipelining (15.4 vs 12.9 Gsps at 128 channels); with two CTAs per
+           SM the second CTA's shared-memory traffic makes it a loss (18.0 vs 20.8 at 256): profiles/r02_notes.md */
+        kp.osc_pipelined = h->nchan <= h->nsm ? 1 : 0;
+        if (const char *e = getenv("B200FSK_OSC_PIPELINED")) kp.osc_pipelined = atoi(e);
         void *args[] = {(void *)&kp};
-        CK(cudaLaunchKernel(pipe_kernel_fn(kp.M, kp.fmt), dim3(h->nchan), dim3(PIPE_THREADS), args, h->smem_pipe, s));
+        CK(cudaLaunchKernel(pipe_kernel_fn(kp.M, kp.fmt, kp.osc_pipelined), dim3(h->nchan), dim3(PIPE_THREADS), args, h->smem_pipe, s));
     } else { fsk_demod_kernel<<<h->nchan, FSK_THREADS, h->smem, s>>>(kp); h->last_kind = 0; }
     CK(cudaGetLastError());
     if (time_it) { CK(cudaEventRecord(h->ev1, s)); h->timed = true; }

@@ -68,6 +68,8 @@ struct FskKParams {
     void *out; long long out_stride; int soft, softinv; int *frame_base;
     FskFrameRec *recs; long long rec_stride; int write_recs;
     int *nframes; long long *consumed; float *eye_raw;
+    float2 *g_ring;             /* pipelined kernel: per-channel oscillator ring in global memory [nchan][M][PIPE_R] */
+    int osc_pipelined;          /* pipelined kernel: software-pipelined oscillator stores (wins with one CTA per SM, loses with two) */
     int lock_nin;               /* fsk.c:724: burst_mode / lock_nin -- the next nin is not adapted */
     long long *prof;            /* FSK_PROFILE builds only: per-phase cycle counters [nchan][16] */
     /* throughput kernel (fsk_wpc_kernel.cuh): channels per CTA, ring geometry, shared-memory byte offsets, global f_int */

@@ -41,8 +41,17 @@
 #define PFLUSH(base, n)
 #endif
 
+#ifndef PIPE_GRING
+#define PIPE_GRING 0            /* experiment, not the default (measured: 19.8 vs 20.8 Gsps at 256 channels, 13.7 vs 12.9 at 128): 1: the oscillator writes its phases to a per-channel ring in GLOBAL memory (L2) instead of shared memory.
+                                   Its stores then queue in the SM's global/local instruction queue, not in the shared-memory queue that the
+                                   FFT / mixer / integrator traffic of both resident CTAs keeps busy; in the ncu capture 40 % of the oscillator
+                                   loop's samples were the first FMUL waiting on registers that queued STS.128 had not read yet
+                                   (profiles/r02_notes.md).  The mixer reads the phases back from L2. */
+#endif
 #define PIPE_THREADS 384        /* 12 warps: OSC 1, TIME 1, DEC 1, CONS 4, EST 4, 1 idle (keeps the oscillator's sub-partition quiet) */
 #define PIPE_R    1024          /* ring capacity per tone, samples (power of two, multiple of PIPE_BLK) */
+#define PIPE_RS   (PIPE_R + 2)  /* row stride: the tones' rows sit 16 B apart in bank space, so the oscillator's two 16-byte stores (one lane per
+                                   tone) no longer collide -- they were 2-way conflicts, 22 % of the kernel's shared-memory wavefronts (profiles/r02) */
 #define PIPE_BLK  (32 * PIPE_NCONS)   /* consumer block = one sample per CONS thread */
 #ifndef PIPE_VARIANT
 #define PIPE_VARIANT 0
@@ -140,11 +149,11 @@ __device__ __forceinline__ void sts128(float2 *dst, float2 a, float2 b)
 #ifndef PIPE_OSC_PIPELINED
 #define PIPE_OSC_PIPELINED 0
 #endif
-__device__ __forceinline__ float2 osc_pairs(float2 ph, const float2 d, float2 *dst, int n)
+__device__ __forceinline__ float2 osc_pairs(float2 ph, const float2 d, float2 *dst, int n, bool pipelined = false)
 {
     int j = 0;
-#if PIPE_OSC_PIPELINED
-    if (n >= 32) {
+#if !PIPE_GRING
+    if ((PIPE_OSC_PIPELINED || pipelined) && n >= 32) {
         float2 a[8], b[8];
         a[0] = cmul_rn(ph, d);
 #pragma unroll
@@ -171,7 +180,7 @@ __device__ __forceinline__ float2 osc_pairs(float2 ph, const float2 d, float2 *d
     return ph;
 }
 
-template <int M, int FMT>
+template <int M, int FMT, bool OSCP>      /* OSCP: software-pipelined oscillator stores (one CTA per SM) */
 __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const FskKParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -209,7 +218,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
     }
     for (int e = tid; e < M * p.tailcap; e += PIPE_THREADS) {           /* integrator memory -> ring slots [-tailcap,0) */
         const int m = e / p.tailcap, i = e - m * p.tailcap;
-        ring[m * PIPE_R + ((i - p.tailcap) & (PIPE_R - 1))] = p.fdc_tail[((long long)c * M + m) * p.tailcap + i];
+        ring[m * PIPE_RS + ((i - p.tailcap) & (PIPE_R - 1))] = p.fdc_tail[((long long)c * M + m) * p.tailcap + i];
     }
     const long long start = p.in_off ? (long long)p.in_off[c] : 0;
     const long long gbase = (long long)c * p.in_stride + start;
@@ -260,7 +269,11 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
     if (role == ROLE_OSC) {
         /* =========================== OSC ======================================================== */
         float2 ph = lane < M ? s_phi0[lane] : make_float2(1.0f, 0.0f);
-        float2 *myring = ring + (lane < M ? lane : 0) * PIPE_R;
+#if PIPE_GRING
+        float2 *myring = p.g_ring + ((size_t)c * M + (lane < M ? lane : 0)) * PIPE_R;
+#else
+        float2 *myring = ring + (lane < M ? lane : 0) * PIPE_RS;
+#endif
         int pos = 0;
         unsigned par_est = 0, par_free = 0, par_pub = 0;
         PDECL
@@ -286,7 +299,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
                         int j = 0;
                         if (pos & 1) { ph = cmul_rn(ph, d); dst[0] = ph; j = 1; }          /* align to a 16-byte pair */
                         const int npair = (n - j) & ~1;
-                        ph = osc_pairs(ph, d, dst + j, npair);
+                        ph = osc_pairs(ph, d, dst + j, npair, OSCP);
                         j += npair;
                         if (j < n) { ph = cmul_rn(ph, d); dst[j] = ph; }
                     }
@@ -482,6 +495,9 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
             int i_done = 0;
             float2 xn = make_float2(0.0f, 0.0f);
             if (ct < min(PIPE_BLK, fend - ck)) xn = load_sample_t<FMT>(p.in, gbase + ck + ct);
+#if PIPE_GRING
+            float2 phn[M]; bool phv = false;                         /* this thread's phases of the next block, fetched early when the oscillator is ahead */
+#endif
             for (int s0 = ck; s0 < fend; s0 += PIPE_BLK) {
                 const int cnt = min(PIPE_BLK, fend - s0);
                 const float2 xv = xn;
@@ -492,11 +508,28 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
                   PTOC(1); }
                 if (ct < cnt) {
                     const int slot = (s0 + ct) & (PIPE_R - 1);
+#pragma unroll
                     for (int m = 0; m < M; ++m) {
-                        const float2 ph = ring[m * PIPE_R + slot];
-                        ring[m * PIPE_R + slot] = cmul_rn(xv, make_float2(ph.x, -ph.y));       /* fsk.c:648 */
+#if PIPE_GRING
+                        const float2 ph = phv ? phn[m] : __ldcg(p.g_ring + ((size_t)c * M + m) * PIPE_R + slot);
+#else
+                        const float2 ph = ring[m * PIPE_RS + slot];
+#endif
+                        ring[m * PIPE_RS + slot] = cmul_rn(xv, make_float2(ph.x, -ph.y));       /* fsk.c:648 */
                     }
                 }
+#if PIPE_GRING
+                {   /* the next block's phases, if the oscillator has already published them (it usually runs ahead): hides the L2 round trip */
+                    const int s1 = s0 + PIPE_BLK;
+                    phv = false;
+                    if (s1 + ct < fend && ld_acq(&s_osc_pos) >= min(s1 + PIPE_BLK, fend)) {
+                        const int slot1 = (s1 + ct) & (PIPE_R - 1);
+#pragma unroll
+                        for (int m = 0; m < M; ++m) phn[m] = __ldcg(p.g_ring + ((size_t)c * M + m) * PIPE_R + slot1);
+                        phv = true;
+                    }
+                }
+#endif
                 group_bar(2, NCT);
                 const int mixed_end = s0 + cnt;
                 int i_hi = 0;
@@ -510,7 +543,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
                     int m, ii;
                     if (M == 2) { m = e >= ni ? 1 : 0; ii = e - m * ni; } else { m = e / ni; ii = e - m * ni; }
                     const int i = i_done + ii, a0 = base + i * step;
-                    const float2 *rg = ring + m * PIPE_R;
+                    const float2 *rg = ring + m * PIPE_RS;
                     float2 acc = make_float2(0.0f, 0.0f);
                     if (pair_path && !par) {
 #pragma unroll 5
@@ -659,7 +692,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 2) fsk_demod_pipe_kernel(const F
     for (int i = tid; i < Ndft; i += PIPE_THREADS) p.Sf[(long long)c * Ndft + i] = Sf_fin[i];
     for (int e = tid; e < M * p.tailcap; e += PIPE_THREADS) {
         const int m = e / p.tailcap, i = e - m * p.tailcap;
-        p.fdc_tail[((long long)c * M + m) * p.tailcap + i] = ring[m * PIPE_R + ((c_end - p.tailcap + i) & (PIPE_R - 1))];
+        p.fdc_tail[((long long)c * M + m) * p.tailcap + i] = ring[m * PIPE_RS + ((c_end - p.tailcap + i) & (PIPE_R - 1))];
     }
     if (tid < M) p.phi_c[c * 4 + tid] = frames > 0 ? desc[(frames - 1) & 3].phi_end[tid] : s_phi0[tid];
     if (tid == 0) {
