@@ -41,6 +41,7 @@ struct b200fsk {
     size_t smem_wpc = 0; bool can_wpc = false, force_wpc = false; int wpc_G = 0, nsm = 0;   /* throughput kernel (many channels per CTA) */
     float2 *d_fint = 0; int *d_abort = 0; int wpc_thresh = 1 << 30;
     float2 *d_gring = 0;
+    size_t fint_bytes = 0; int l2_persist = 0; size_t l2_window = 0; float l2_ratio = 0.0f;   /* L2 persistence window over the f_int slots */
     unsigned short *d_invperm = 0;
     std::vector<float> h_fest;         /* LUT: tone estimate in Hz per table index */
     /* device tables */
@@ -320,6 +321,22 @@ extern "C" int b200fsk_create(b200fsk_t **out, const b200fsk_cfg_t *cfg, int nch
             const int slots = (WPC_CTAS == 1) ? h->nsm : nchan;       /* nchan >= number of CTAs */
             kp.w_fint_slots = slots;
             CKH(zalloc(&h->d_fint, (size_t)slots * WPC_MAXG * M * nfi));
+            h->fint_bytes = (size_t)slots * WPC_MAXG * M * nfi * sizeof(float2);
+            /* The f_int slots are rewritten once per frame by the CTA that owns them and read back by the same warp: a hot set of
+               #SMs x 15 x 24 KB (53 MB at the RS41 line) that the input stream would otherwise push out of L2 between rewrites
+               (ncu: 8 B/sample of extra DRAM writes).  Pin it with a persisting access-policy window on the launching stream. */
+            const char *e = getenv("B200FSK_L2PERSIST");
+            int maxp = 0, maxw = 0;
+            cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, device);
+            cudaDeviceGetAttribute(&maxw, cudaDevAttrMaxAccessPolicyWindowSize, device);
+            if ((!e || atoi(e)) && maxp > 0 && maxw > 0 && WPC_CTAS == 1) {
+                const size_t want = h->fint_bytes < (size_t)maxp ? h->fint_bytes : (size_t)maxp;
+                if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+                    h->l2_persist = 1;
+                    h->l2_window = h->fint_bytes < (size_t)maxw ? h->fint_bytes : (size_t)maxw;
+                    h->l2_ratio = (float)((double)want / (double)h->l2_window); if (h->l2_ratio > 1.0f) h->l2_ratio = 1.0f;
+                } else cudaGetLastError();
+            }
         }
         CKH(zalloc(&h->d_abort, 1));
         kp.w_fint = h->d_fint; kp.w_abort = h->d_abort;
@@ -455,6 +472,12 @@ static int launch(b200fsk *h, FskKParams &kp, cudaStream_t s, bool time_it)
         if (G < 1) G = 1;
         kp.w_G = G;
         const size_t smem = (size_t)kp.w_chan0 + (size_t)G * kp.w_chan_stride;
+        if (h->l2_persist) {
+            cudaStreamAttrValue av; memset(&av, 0, sizeof av);
+            av.accessPolicyWindow.base_ptr = h->d_fint; av.accessPolicyWindow.num_bytes = h->l2_window; av.accessPolicyWindow.hitRatio = h->l2_ratio;
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting; av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            if (cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) { cudaGetLastError(); h->l2_persist = 0; }
+        }
         void *args[] = {(void *)&kp};
         CK(cudaLaunchKernel(wpc_kernel_fn(kp.M, kp.fmt), dim3((h->nchan + G - 1) / G), dim3((G + 1) * 32), args, smem, s));
         h->last_kind = 2;

@@ -118,6 +118,22 @@ template <int FMT> __device__ __forceinline__ float2 load_sample_t(const void *i
     return make_float2(__fdiv_rn((float)s, 1000.0f), 0.0f);
 }
 
+/* The LAST use of a sample (the mixer's read, one frame after the estimator's): evict-first, so that it leaves L2 to the samples that are
+ * still waiting for their second read. */
+template <int FMT> __device__ __forceinline__ float2 load_sample_last(const void *in, long long idx)
+{
+    if (FMT == 1) return __ldcs((const float2 *)in + idx);
+    if (FMT == 0) {
+        const short2 s = __ldcs((const short2 *)in + idx);
+        return make_float2(__fdiv_rn((float)s.x, 1000.0f), __fdiv_rn((float)s.y, 1000.0f));
+    }
+    if (FMT == 2) {
+        const uchar2 u = __ldcs((const uchar2 *)in + idx);
+        return make_float2(__fdiv_rn(__fsub_rn((float)u.x, 127.0f), 128.0f), __fdiv_rn(__fsub_rn((float)u.y, 127.0f), 128.0f));
+    }
+    const short s = __ldcs((const short *)in + idx);
+    return make_float2(__fdiv_rn((float)s, 1000.0f), 0.0f);
+}
 /* In-place mixed-radix DIT FFT of one warp's buffer; F already holds the permuted, windowed input.
  * Same butterflies, twiddle indices and operand order as kiss_fft's kf_bfly2 / kf_bfly4 forward
  * (kiss_fft.c:21-42, 44-90), executed stage by stage bottom-up.  PAD inserts one float2 of padding per 8

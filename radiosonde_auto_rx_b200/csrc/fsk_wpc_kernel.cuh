@@ -277,7 +277,7 @@ __global__ void __launch_bounds__((WPC_MAXG + 1) * 32, WPC_CTAS) fsk_wpc_kernel(
         float acc = 0.0f;                                            /* lanes 0/1: re/im of the timing sum (fsk.c:686-698) */
         float2 xn[4];                                                /* the next block's samples, fetched one block ahead */
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { const int t = u * 32 + lane; xn[u] = (t < BLK && ck + t < fend) ? load_sample_t<FMT>(p.in, gbase + ck + t) : make_float2(0.0f, 0.0f); }
+        for (int u = 0; u < 4; ++u) { const int t = u * 32 + lane; xn[u] = (t < BLK && ck + t < fend) ? load_sample_last<FMT>(p.in, gbase + ck + t) : make_float2(0.0f, 0.0f); }
         for (int s0 = ck; s0 < fend; s0 += BLK) {
             const int cnt = min(BLK, fend - s0);
             /* oscillator output not there yet: spend the time on the next frame's FFTs */
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__((WPC_MAXG + 1) * 32, WPC_CTAS) fsk_wpc_kernel(
                 for (int u = 0; u < 4; ++u) {
                     xv[u] = xn[u];
                     const int t = BLK + u * 32 + lane;
-                    xn[u] = (u * 32 + lane < BLK && s0 + t < fend) ? load_sample_t<FMT>(p.in, gbase + s0 + t) : make_float2(0.0f, 0.0f);
+                    xn[u] = (u * 32 + lane < BLK && s0 + t < fend) ? load_sample_last<FMT>(p.in, gbase + s0 + t) : make_float2(0.0f, 0.0f);
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
