@@ -424,6 +424,98 @@ def run_dft_secondary(args, local: int):
 
 
 # ---------------------------------------------------------------------------------------------------
+# --scatter: the collective path (BASELINE.json configs[3]: channels sharded across the GPUs of one box via NCCL scatter)
+# ---------------------------------------------------------------------------------------------------
+def run_scatter(args):
+    """Rank 0 holds the whole capture (world x C channels, cs16, the production sample format) in ITS HBM -- as if one GPU had received
+    it -- and scatters it by channel block, one time block after the other (NCCL over NVLink); every rank demodulates block t while
+    block t+1 is in flight (two receive buffers, copy stream + compute stream).  One step = T time blocks.  Reports whole-job
+    Msamples/s (max over ranks of CUDA-event time) and the scatter rate out of rank 0 against the measured NVLink peer bandwidth.
+    Block ends drop the sub-frame remainder like every b200fsk_demod_device call (the modem state carries over)."""
+    import torch
+    import torch.distributed as dist
+    from radiosonde_auto_rx_b200 import fsk
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    C, B, T = args.scatter_channels, args.scatter_block, args.scatter_blocks
+    dev = torch.device("cuda", local)
+    cap = None
+    if rank == 0:                                   # the capture: world*C channels x T*B samples, generated once (64 distinct channels, repeated)
+        base = torch.from_numpy(gen_channels(0, 64, T * B)).to(dev)
+        cap = base.repeat((world * C + 63) // 64, 1, 1)[: world * C].contiguous()          # [world*C, T*B, 2] int16
+        del base
+    b = fsk.FskBatch(FS, RS, M, P, NSYM, 1000, MASK, LO, HI, 1, nchan=C, device=local)
+    maxf = b.max_frames(B)
+    d_out = torch.zeros((C, maxf * b.Nbits), dtype=torch.float32, device=dev)
+    recv = [torch.empty((C, B, 2), dtype=torch.int16, device=dev) for _ in range(2)]
+    copy_s, comp_s = torch.cuda.Stream(), torch.cuda.Stream()
+    ev_rx = [torch.cuda.Event() for _ in range(2)]
+    ev_done = [torch.cuda.Event() for _ in range(2)]
+
+    def post_scatter(t):
+        """block t -> recv[t % 2] on the copy stream (after the kernel that last read that buffer)"""
+        with torch.cuda.stream(copy_s):
+            copy_s.wait_event(ev_done[t % 2])
+            if world > 1:
+                # NCCL has no 16-bit integer type: one cs16 sample (I,Q) travels as one int32
+                lst = [cap[r * C:(r + 1) * C, t * B:(t + 1) * B].contiguous().view(torch.int32) for r in range(world)] if rank == 0 else None
+                dist.scatter(recv[t % 2].view(torch.int32), lst, src=0)
+            else:
+                recv[t % 2].copy_(cap[:, t * B:(t + 1) * B])
+            ev_rx[t % 2].record(copy_s)
+
+    def one_step():
+        post_scatter(0)
+        for t in range(T):
+            if t + 1 < T:
+                post_scatter(t + 1)
+            comp_s.wait_event(ev_rx[t % 2])
+            b.demod_device(recv[t % 2], "cs16", B, d_out, soft=True, in_stride=B, out_stride=maxf * b.Nbits, stream=comp_s)
+            ev_done[t % 2].record(comp_s)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(max(args.warmup, 3)):            # warms up the NCCL communicator too
+        one_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = b.launches
+    e0.record(comp_s)
+    for _ in range(args.steps):
+        one_step()
+    e1.record(comp_s)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    frames, consumed = b.counts()
+    tv = torch.tensor([ms], dtype=torch.float64, device=dev)
+    sv = torch.tensor([float(consumed.sum())], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tv, op=dist.ReduceOp.MAX); dist.all_reduce(sv, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        fed = float(world) * C * T * B * args.steps                       # samples scattered and demodulated
+        value = fed / (float(tv[0]) * 1e-3) / 1e6
+        sent = float(world - 1) * C * T * B * 4 * args.steps              # bytes that left rank 0 over NVLink
+        line = {"metric": METRIC, "mode": "scatter", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": float(tv[0]) / args.steps, "higher_is_better": True, "scaling": "weak", "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"NCCL scatter of a cs16 capture held by rank 0: {world} x {C} RS41-prod channels, {T} time blocks of {B} samples per step, "
+                                       "scatter of block t+1 overlapped with the demodulation of block t",
+                           "consumed_last_block_samples": float(sv[0])},
+                "collective": {"op": "torch.distributed.scatter (NCCL grouped send/recv), src rank 0", "bytes_out_of_rank0_per_step": sent / args.steps,
+                               "rate_GBs": sent / (float(tv[0]) * 1e-3) / 1e9, "nvlink_peer_copy_GBs_measured": 770.0,
+                               "note": "rate = bytes leaving rank 0 / whole step time (the scatter overlaps the kernels; it is not timed alone)"},
+                "gpu_launches": int(b.launches - l0), "host": numa}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -652,6 +744,10 @@ def main():
     ap.add_argument("--sweep-channels", type=int, nargs="*", default=[256, 1024, 4096])
     ap.add_argument("--sweep-nsamp", type=int, default=1 << 18)
     ap.add_argument("--sweep-steps", type=int, default=3)
+    ap.add_argument("--scatter", action="store_true", help="time the NCCL scatter + demod path (rank 0 holds the capture) instead of the resident-input bench")
+    ap.add_argument("--scatter-channels", type=int, default=128, help="channels per GPU (BASELINE configs[3]: 1024 channels over 8 GPUs)")
+    ap.add_argument("--scatter-block", type=int, default=1 << 17)
+    ap.add_argument("--scatter-blocks", type=int, default=8)
     ap.add_argument("--no-secondary", action="store_true", help="skip the dft_detect workload (BASELINE configs[2])")
     ap.add_argument("--dft-channels", type=int, default=4096)
     ap.add_argument("--dft-nsamp", type=int, default=1 << 18)
@@ -662,6 +758,8 @@ def main():
         return 0
     if args.warmup < 3:
         args.warmup = 3
+    if args.scatter:
+        return run_scatter(args)
     return run_ours(args)
 
 
