@@ -105,8 +105,14 @@ int main(int argc, char **argv)
     while (!eof || have >= nin) {
         /* block until one more frame's worth is available, then take whatever else is already there */
         long got = 0;
-        if (!eof) {
-            long want = CHUNK, need = nin > have ? nin - have : 0;
+        /* frames allowed in this call: stop on the frame that prints statistics so that they describe that frame */
+        int maxf = 0;
+        if (testframes) maxf = 1; else if (stats) maxf = stats_ctr < 0 ? 1 : stats_ctr + 2;
+        /* Read only what this call can consume: with a frame cap, more than maxf frames' worth would pile up inside the
+           handle (O(file) memory, quadratic tail copies on file input); and never block on read() while a whole frame is already there. */
+        long want = CHUNK, need = nin > have ? nin - have : 0;
+        if (maxf > 0) { want = (long)maxf * info.nin_max - have; if (want > CHUNK) want = CHUNK; if (want < need) want = need; }
+        if (!eof && want > 0 && need > 0) {
             while (got < want) {
                 ssize_t r = read(fdin, inbuf + got * es, (size_t)(want - got) * es);
                 if (r < 0 && errno == EINTR) continue;
@@ -118,9 +124,6 @@ int main(int argc, char **argv)
                 if (got >= need) break;
             }
         }
-        /* frames allowed in this call: stop on the frame that prints statistics so that they describe that frame */
-        int maxf = 0;
-        if (testframes) maxf = 1; else if (stats) maxf = stats_ctr < 0 ? 1 : stats_ctr + 2;
         int frames = 0;
         if (b200fsk_push_host(h, inbuf, fmt, got, got, maxf, outbuf, maxf_cap * info.Nbits, soft, softinv, &frames) != B200FSK_OK) {
             fprintf(stderr, "fsk_demod: %s\n", b200fsk_last_error()); exit(1);
