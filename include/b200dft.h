@@ -64,6 +64,8 @@ typedef struct {
  * dft_detect.c:1132-1137, which is what auto_rx always passes); opt_dc is --dc. */
 int  b200dft_create(b200dft_t **out, int sample_rate, double bw_khz, int opt_dc, int nchan, int device);
 void b200dft_destroy(b200dft_t *h);
+/* `--ths x` (dft_detect.c:1426-1431): replace the per-header detection thresholds by one value (before the first run) */
+int  b200dft_set_threshold(b200dft_t *h, double ths);
 int  b200dft_info(const b200dft_t *h, b200dft_info_t *info);
 const char *b200dft_last_error(void);
 

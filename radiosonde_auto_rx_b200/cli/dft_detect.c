@@ -16,7 +16,7 @@
 int main(int argc, char **argv)
 {
     int verbose = 0, cont = 0, silent = 0, iq = 0, dc = 0, sr = 0, bits = 0, pcmraw = 0, wide = 0;
-    double tl = -1.0, bw = 0.0, fq = 0.0;
+    double tl = -1.0, bw = 0.0, fq = 0.0, ths = 0.0; int have_ths = 0;
     for (char **a = argv + 1; *a; ++a) {
         if (!strcmp(*a, "-h") || !strcmp(*a, "--help")) {
             fprintf(stderr, "%s [options] - <sr> <bits>   (raw IQ on stdin)\n  options:\n       -v          (verbose)\n       -c          (continuous)\n"
@@ -35,7 +35,7 @@ int main(int argc, char **argv)
             if (sr < 1 || (bits != 8 && bits != 16 && bits != 32)) { fprintf(stderr, "- <sr> <bs>\n"); return -1; }
             pcmraw = 1;
         } else if (!strcmp(*a, "--IQ")) { if (!*++a) return -1; fq = atof(*a); iq = 1; wide = 1; }
-        else if (!strcmp(*a, "--ths")) { fprintf(stderr, "dft_detect(b200): option %s not supported\n", *a); return -50; }
+        else if (!strcmp(*a, "--ths")) { if (!*++a) return -50; ths = atof(*a); have_ths = 1; }
         else if (!strcmp(*a, "--min") || !strcmp(*a, "-L") || !strcmp(*a, "-d2") || !strcmp(*a, "--ch2")) { fprintf(stderr, "dft_detect(b200): option %s not supported\n", *a); return -50; }
         else { fprintf(stderr, "dft_detect(b200): file/WAV input not supported, use: --iq --bw <kHz> - <sr> <bits>\n"); return -50; }
     }
@@ -44,6 +44,7 @@ int main(int argc, char **argv)
     b200dft_t *h = NULL;
     const int crc = wide ? b200dft_create_wideband(&h, sr, bw, dc, 1, 0) : b200dft_create(&h, sr, bw, dc, 1, 0);
     if (crc != B200DFT_OK) { fprintf(stderr, "error: init buffers (%s)\n", b200dft_last_error()); return -50; }
+    if (have_ths && b200dft_set_threshold(h, ths) != B200DFT_OK) { fprintf(stderr, "dft_detect(b200): %s\n", b200dft_last_error()); return -50; }
     if (wide) {                                         /* -t counts IF samples (:1494) = (tl+1)*sr input samples, sr = IF*dec */
         b200dft_wbinfo_t wb; b200dft_wideband_info(h, &wb);
         fprintf(stderr, "IF: %d\n", wb.if_sr); fprintf(stderr, "dec: %d\n", wb.decM);      /* :1067-1068 */

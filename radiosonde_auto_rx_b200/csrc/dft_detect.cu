@@ -486,6 +486,7 @@ struct b200dft {
     int N, K, L, M, delay, lpIQtaps, lpFMtaps, nact, maxcnt;
     std::vector<HdrDev> hdr; std::vector<int> act;      /* active header rows */
     float spb[NRS]; int hLen[NRS], Lj[NRS];
+    float thres[NRS];              /* detection thresholds: rs_hdr[].thres, or the --ths override for every header (:1426-1431) */
     float *d_ws_lpIQ = 0, *d_ws_lpFM = 0, *d_match = 0; HdrDev *d_hdr = 0;
     float2 *d_avg = 0; float *d_fm_filt = 0, *d_fm_raw = 0; BlkRes *d_res = 0; void *d_iq = 0;
     long long cap_samp = 0, cap_samp_run = 0, cap_iq_bytes = 0; int cap_blk = 0, cap_avg = 0;
@@ -533,6 +534,7 @@ extern "C" int b200dft_create(b200dft_t **out, int sample_rate, double bw_khz, i
     if (device < 0 || device >= ndev) return fail(B200DFT_ERANGE, "device");
     CK(cudaSetDevice(device));
     b200dft *h = new b200dft();
+    for (int j = 0; j < NRS; j++) h->thres[j] = HDR[j].thres;
     h->sr = sample_rate; h->opt_dc = opt_dc ? 1 : 0; h->nchan = nchan; h->device = device; h->bw_khz = bw_khz;
     const int sr = sample_rate;
     /* init_buffers(), --iq branch (dft_detect.c:1113-1156) */
@@ -579,7 +581,7 @@ extern "C" int b200dft_create(b200dft_t **out, int sample_rate, double bw_khz, i
         for (int i = 0; i < Lj; i++) match[i] /= nm;
         HdrDev hd; memset(&hd, 0, sizeof hd);
         hd.j = j; hd.L = Lj; hd.Lpad = (Lj + CORR_R - 1) / CORR_R * CORR_R; hd.hLen = h->hLen[j]; hd.use_raw = HDR[j].lpIQ == 3;
-        hd.lpFM = HDR[j].lpFM; hd.match_off = (int)match_all.size(); hd.spb = spb; hd.thres = HDR[j].thres;
+        hd.lpFM = HDR[j].lpFM; hd.match_off = (int)match_all.size(); hd.spb = spb; hd.thres = HDR[j].thres; h->thres[j] = HDR[j].thres;
         for (int i = 0; i < hd.hLen; i++) hd.bits[i] = bits[i] & 1;
         for (int i = 0; i < hd.Lpad; i++) match_all.push_back(i < Lj ? match[i] : 0.0f);
         h->hdr.push_back(hd); h->act.push_back(j);
@@ -604,6 +606,16 @@ extern "C" int b200dft_create(b200dft_t **out, int sample_rate, double bw_khz, i
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 4; i++) CK(cudaEventCreate(&h->ev[i]));
     *out = h;
+    return B200DFT_OK;
+}
+
+extern "C" int b200dft_set_threshold(b200dft_t *h, double ths)
+{
+    if (!h) return fail(B200DFT_EINVAL, "null");
+    CK(cudaSetDevice(h->device));
+    for (int j = 0; j < NRS; j++) h->thres[j] = (float)ths;               /* --ths x: one threshold for every header (:1426-1431) */
+    for (size_t a = 0; a < h->hdr.size(); a++) h->hdr[a].thres = (float)ths;
+    CK(cudaMemcpy(h->d_hdr, h->hdr.data(), h->hdr.size() * sizeof(HdrDev), cudaMemcpyHostToDevice));
     return B200DFT_OK;
 }
 
@@ -641,7 +653,7 @@ static void chan_finish(ChanRun &s)
 }
 static void chan_report(const b200dft *h, ChanRun &s, int j)                 /* the printf block, :1611-1642 */
 {
-    if (s.mv[j] > HDR[j].thres || s.mv[j] < -HDR[j].thres) {
+    if (s.mv[j] > h->thres[j] || s.mv[j] < -h->thres[j]) {
         if (s.out->ndet < B200DFT_MAXDET) {
             b200dft_det_t *d = &s.out->dets[s.out->ndet];
             d->hdr = j; d->tn = s.tn[j]; d->score = s.mv[j]; d->pos = s.mv_pos[j]; d->df_hz = s.dfv[j] * (h->wide ? h->sr_base : h->sr); d->m10 = s.frm2 & 0xFFFF;
@@ -698,7 +710,7 @@ static void chan_advance(b200dft *h, ChanRun &s, const BlkRes *res, int nblk_lau
                 if (j != IDX_IMETAFSK) continue;
                 const float mvj = rb[a].mp > 0 ? rb[a].score : s.mv[j];
                 const unsigned pj = rb[a].mp > 0 ? rb[a].pos : s.mv_pos[j];
-                if (rb[a].mp > 0 && (mvj > HDR[j].thres || mvj < -HDR[j].thres) && pj > s.mv_pos[j] && rb[a].herrs < HDR[j].herrs) { s.starved = true; return; }
+                if (rb[a].mp > 0 && (mvj > h->thres[j] || mvj < -h->thres[j]) && pj > s.mv_pos[j] && rb[a].herrs < HDR[j].herrs) { s.starved = true; return; }
             }
         }
         for (int a = 0; a < nact; a++) {
@@ -712,7 +724,7 @@ static void chan_advance(b200dft *h, ChanRun &s, const BlkRes *res, int nblk_lau
         int header_found = 0;
         for (int a = 0; a < nact; a++) {
             const int j = h->act[a];
-            if (!(s.mp[j] > 0 && (s.mv[j] > HDR[j].thres || s.mv[j] < -HDR[j].thres))) continue;
+            if (!(s.mp[j] > 0 && (s.mv[j] > h->thres[j] || s.mv[j] < -h->thres[j]))) continue;
             if (!(s.mv_pos[j] > s.mv0_pos[j])) continue;
             if (!(rb[a].herrs < HDR[j].herrs)) continue;
             if (j == 6) {                                                       /* M10 / M20 (:1526-1540) */

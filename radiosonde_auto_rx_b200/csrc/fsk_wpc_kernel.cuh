@@ -420,12 +420,26 @@ __global__ void __launch_bounds__((WPC_MAXG + 1) * 32, WPC_CTAS) fsk_wpc_kernel(
         __syncwarp();
         if (!nan) {
             const float omf = __fsub_rn(1.0f, fract);
-            for (int i = lane; i < nsym; i += 32) {
-                const int st = (i + 1) * P;
+            constexpr int DB = (M == 2) ? 4 : 2;                      /* symbols per lane whose L2 reads are in flight together */
+            for (int i0 = lane; i0 < nsym; i0 += 32 * DB) {
+                float2 fa[DB][M], fb[DB][M];
+#pragma unroll
+                for (int u = 0; u < DB; ++u) {
+                    const int i = i0 + 32 * u, st = (i + 1) * P;
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        fa[u][m] = i < nsym ? __ldcg(fintg + (size_t)m * nfi + st + low) : make_float2(0.0f, 0.0f);
+                        fb[u][m] = i < nsym ? __ldcg(fintg + (size_t)m * nfi + st + high) : make_float2(0.0f, 0.0f);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < DB; ++u) {
+                const int i = i0 + 32 * u;
+                if (i >= nsym) break;
                 float tmax[4];
 #pragma unroll
                 for (int m = 0; m < M; ++m) {
-                    const float2 a = __ldcg(fintg + (size_t)m * nfi + st + low), b = __ldcg(fintg + (size_t)m * nfi + st + high);
+                    const float2 a = fa[u][m], b = fb[u][m];
                     const float2 t = make_float2(__fadd_rn(__fmul_rn(omf, a.x), __fmul_rn(fract, b.x)),
                                                  __fadd_rn(__fmul_rn(omf, a.y), __fmul_rn(fract, b.y)));
                     tmax[m] = mag2_rn(t);
@@ -451,7 +465,8 @@ __global__ void __launch_bounds__((WPC_MAXG + 1) * 32, WPC_CTAS) fsk_wpc_kernel(
                     }
                 }
             }
-        } else {                                                     /* stale frame, fsk_demod.c:424-433 */
+            }
+                } else {                                                     /* stale frame, fsk_demod.c:424-433 */
             for (int i = lane; i < p.Nbits; i += 32) {
                 if (p.soft) {
                     float *o = (float *)outb;

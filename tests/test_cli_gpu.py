@@ -61,7 +61,8 @@ def test_fsk_demod_cli_usage_error(cuda):
 
 
 @needs_ref
-@pytest.mark.parametrize("kind,extra", [("RS41", []), ("DFM9", ["-c", "-v"]), ("M10", ["-v"]), ("noise", ["-t", "1"])])
+@pytest.mark.parametrize("kind,extra", [("RS41", []), ("DFM9", ["-c", "-v"]), ("M10", ["-v"]), ("noise", ["-t", "1"]),
+                                        ("RS41", ["-c", "-v", "--ths", "0.9"]), ("DFM9", ["-c", "-v", "--ths", "0.5"])])
 def test_dft_detect_cli_matches_reference(cuda, kind, extra):
     n = 110_000
     iq = siggen.noise_iq(3, n) if kind == "noise" else siggen.fm_header_iq(60, n, kind, snr_db=17.0)

@@ -256,6 +256,33 @@ def test_more_channels_than_resident_ctas(cuda, mode):
         assert frames[c] == len(recs) and out[c, : frames[c] * b.Nbits].tobytes() == ref.tobytes(), c
 
 
+def test_full_ctas_of_the_throughput_kernel_two_waves(cuda):
+    """2300 channels = 15 channel warps per CTA, more CTAs than SMs (two waves), the last CTA only partly filled; ragged content and
+    per-channel stream lengths (device path with in_off): every checked channel bit-exact, and the kernel really is fsk_wpc_kernel."""
+    import torch
+    cfg = po.RS41
+    nchan, nsamp = 2300, 30_000
+    base = siggen.fsk_batch(4242, 64, nsamp)
+    base[3] = siggen.noise_iq(9, nsamp)
+    iq = np.tile(base, ((nchan + 63) // 64, 1, 1))[:nchan].copy()
+    rng = np.random.default_rng(1)
+    off = rng.integers(0, 2500, nchan).astype(np.int32)            # every channel starts somewhere else in its row
+    off[:4] = 0
+    b = make_batch(cfg, nchan)
+    x = torch.from_numpy(iq).cuda()
+    d_off = torch.from_numpy(off).cuda()
+    maxf = b.max_frames(nsamp)
+    d_out = torch.zeros((nchan, maxf * b.Nbits), dtype=torch.float32, device="cuda")
+    b.demod_device(x, "cs16", nsamp, d_out, soft=True, in_stride=nsamp, out_stride=maxf * b.Nbits, d_in_off=d_off)
+    frames, consumed = b.counts()
+    assert b.last_kernel() == "fsk_wpc_kernel"
+    out = d_out.cpu().numpy()
+    for c in list(range(0, nchan, 61)) + [3, 67, 2285, 2299]:
+        ref, cons, recs = po.Oracle(cfg).run_stream(iq[c, off[c]:])
+        assert frames[c] == len(recs) and consumed[c] == cons, c
+        assert out[c, : frames[c] * b.Nbits].tobytes() == ref.tobytes(), c
+
+
 def test_nin_dependent_window_count_uses_the_serial_kernel(cuda):
     """Nsym=64 at Ts=10: floor(nin/64) is 9 for nin=635 and 10 for nin=645, so the number of FFT windows depends on nin and
     the pipelined kernel is not eligible -> the library must fall back to the serial kernel transparently."""
