@@ -146,7 +146,7 @@ def _ref_pump(iq_row: np.ndarray, want_out: bool, passes: int = 1):
     return (out if want_out else None), cons
 
 
-def _worker(core, chans, iq, start_evt, q, repeats):
+def _worker(core, chans, iq, start_evt, q, repeats, bar=None):
     try:
         os.sched_setaffinity(0, {core})
     except OSError:
@@ -156,6 +156,8 @@ def _worker(core, chans, iq, start_evt, q, repeats):
     start_evt.wait()
     res = []
     for _ in range(repeats):
+        if bar is not None:
+            bar.wait()                                 # every pass starts on all processes together: a pass's wall time is one number
         t0 = time.perf_counter()
         n = 0
         for c in chans:
@@ -175,10 +177,11 @@ def time_reference(iq: np.ndarray, repeats: int = 3, ncores: int | None = None):
     nproc = min(len(cpus), nchan)
     ctx = mp.get_context("fork")
     q, start = ctx.Queue(), ctx.Event()
+    bar = ctx.Barrier(nproc)
     procs = []
     for r in range(nproc):
         chans = list(range(r, nchan, nproc))
-        pr = ctx.Process(target=_worker, args=(cpus[r], chans, iq, start, q, repeats))
+        pr = ctx.Process(target=_worker, args=(cpus[r], chans, iq, start, q, repeats, bar))
         pr.start()
         procs.append(pr)
     ready = 0
