@@ -179,7 +179,7 @@ long b200fsk_launch_count(const b200fsk_t *h);
 float b200fsk_last_kernel_ms(b200fsk_t *h);
 /* which frame kernel the handle's most recent launch used: 0 = fsk_demod_kernel (one stage at a time), 1 = fsk_demod_pipe_kernel
  * (one warp-specialised CTA per channel: <= 2 channels per SM), 2 = fsk_wpc_kernel (up to 15 channels per CTA sharing one
- * lane-per-chain oscillator warp: large batches); -1 before the first launch.  All three produce identical bits. */
+ * lane-per-chain oscillator warp: large batches), 3 = fsk_duo_kernel (two channels per CTA, one CTA per SM); -1 before the first launch.  All three produce identical bits. */
 int b200fsk_last_kernel_kind(const b200fsk_t *h);
 
 #ifdef __cplusplus

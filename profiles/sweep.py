@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Throughput of the batched fsk_demod kernels vs channel count (device-resident float2 input, RS41 production line).
-usage: sweep.py [nsamp_log2] mode:nchan [mode:nchan ...]     mode = auto | pipe | wpc | serial
+usage: sweep.py [nsamp_log2] mode:nchan [mode:nchan ...]     mode = auto | pipe | wpc | duo | serial
 Channels beyond 256 repeat the same 256 seeded streams (throughput only; parity is tests/)."""
 import os, sys, json, time
 import numpy as np

@@ -21,6 +21,7 @@
 #include "../../include/b200fsk.h"
 #include "fsk_pipe_kernel.cuh"
 #include "fsk_wpc_kernel.cuh"
+#include "fsk_duo_kernel.cuh"
 
 static thread_local std::string g_err;
 static int fail(int code, const char *fmt, ...)
@@ -41,6 +42,7 @@ struct b200fsk {
     size_t smem_wpc = 0; bool can_wpc = false, force_wpc = false; int wpc_G = 0, nsm = 0;   /* throughput kernel (many channels per CTA) */
     float2 *d_fint = 0; int *d_abort = 0; int wpc_thresh = 1 << 30;
     float2 *d_gring = 0;
+    bool can_duo = false, force_duo = false, duo_auto = false; size_t smem_duo = 0;   /* two channels per CTA, one CTA per SM */
     size_t fint_bytes = 0; int l2_persist = 0; size_t l2_window = 0; float l2_ratio = 0.0f;   /* L2 persistence window over the f_int slots */
     unsigned short *d_invperm = 0;
     std::vector<float> h_fest;         /* LUT: tone estimate in Hz per table index */
@@ -112,6 +114,14 @@ static const void *wpc_kernel_fn(int M, int fmt)
     static const pipe_fn_t tab[2][4] = {
         {fsk_wpc_kernel<2, 0>, fsk_wpc_kernel<2, 1>, fsk_wpc_kernel<2, 2>, fsk_wpc_kernel<2, 3>},
         {fsk_wpc_kernel<4, 0>, fsk_wpc_kernel<4, 1>, fsk_wpc_kernel<4, 2>, fsk_wpc_kernel<4, 3>}};
+    return (const void *)tab[M == 4 ? 1 : 0][fmt & 3];
+}
+
+static const void *duo_kernel_fn(int M, int fmt)
+{
+    static const pipe_fn_t tab[2][4] = {
+        {fsk_duo_kernel<2, 0>, fsk_duo_kernel<2, 1>, fsk_duo_kernel<2, 2>, fsk_duo_kernel<2, 3>},
+        {fsk_duo_kernel<4, 0>, fsk_duo_kernel<4, 1>, fsk_duo_kernel<4, 2>, fsk_duo_kernel<4, 3>}};
     return (const void *)tab[M == 4 ? 1 : 0][fmt & 3];
 }
 
@@ -303,6 +313,28 @@ extern "C" int b200fsk_create(b200fsk_t **out, const b200fsk_cfg_t *cfg, int nch
         if (force && (!strcmp(force, "serial") || !strcmp(force, "pipe"))) h->can_wpc = false;
         if (force && !strcmp(force, "wpc") && !h->can_wpc) fprintf(stderr, "b200fsk: B200FSK_KERNEL=wpc but this modem is not eligible\n");
     }
+    {   /* two-channels-per-CTA kernel: needs the fused 128-point FFT and the pipeline's window-count condition */
+        const int nmin = N - Ts / 2, nmax = N + Ts / 2;
+        const int f0 = (int)floor((float)nmin / (Ndft / 2)), f1 = (int)floor((float)nmax / (Ndft / 2));
+        size_t q = 0;
+        auto take = [&](size_t bytes) { size_t r = q; q += (bytes + 15) & ~(size_t)15; return (int)r; };
+        kp.d_hann = take(Ndft * 4); kp.d_tw = take(Ndft * 8); kp.d_mask = take(Ndft * 4); kp.d_phift = take((size_t)nfi * 8);
+        q = (q + 127) & ~(size_t)127; kp.d_chan0 = (int)q;
+        size_t o2 = 0;
+        auto t2 = [&](size_t bytes) { size_t r = o2; o2 += (bytes + 15) & ~(size_t)15; return (int)r; };
+        kp.d_tcap = (DUO_BLK + 3 * Ts + 8) & ~3;
+        kp.d_ring_off = t2((size_t)M * DUO_RS * 8); kp.d_fint_off = t2((size_t)2 * M * nfi * 8); kp.d_fft_off = t2((size_t)DUO_NE * 4 * F128_STRIDE * 8);
+        kp.d_mag_off = t2((size_t)DUO_MAGSETS * 4 * F128_MSTRIDE * 4); kp.d_Sf_off = t2((size_t)2 * Ndft * 4); kp.d_scr_off = t2(Ndft * 4);
+        kp.d_term_off = t2((size_t)2 * kp.d_tcap * 4); kp.d_smax_off = t2((size_t)Nsym * 8);
+        o2 = (o2 + 127) & ~(size_t)127; o2 += (M == 2) ? 32 : 64;          /* bank offset between the two channels' rings (oscillator stores) */
+        kp.d_chan_stride = (int)o2;
+        h->smem_duo = (size_t)kp.d_chan0 + (size_t)DUO_G * o2;
+        h->can_duo = (Ndft == 128) && (f0 == f1) && (f0 - 1 >= 1) && (3 * Ts + 2 * DUO_BLK + 16 <= DUO_RN) && (nfi >= 2) && (32 / M >= DUO_G) &&
+                     (h->smem_duo + 4096 <= (size_t)maxsmem);
+        const char *force = getenv("B200FSK_KERNEL");
+        h->force_duo = h->can_duo && force && !strcmp(force, "duo");
+        if (force && strcmp(force, "duo")) h->can_duo = false;
+    }
     const bool serial_fits = h->smem + 256 <= (size_t)maxsmem;
     if (h->use_pipe && h->smem_pipe + 1024 > (size_t)maxsmem) h->use_pipe = false;
     if (!h->use_pipe && !serial_fits) { b200fsk_destroy(h); return fail(B200FSK_ENOMEM, "frame working set %zu B exceeds shared memory %d B", h->smem, maxsmem); }
@@ -315,6 +347,7 @@ extern "C" int b200fsk_create(b200fsk_t **out, const b200fsk_cfg_t *cfg, int nch
         }
     }
     if (h->use_pipe) { CKH(zalloc(&h->d_gring, (size_t)nchan * M * PIPE_R)); kp.g_ring = h->d_gring; }
+    if (h->can_duo) { for (int f = 0; f < 4; ++f) CKH(allow_max_smem(duo_kernel_fn(M, f), maxsmem)); if (!h->d_abort) { CKH(zalloc(&h->d_abort, 1)); kp.w_abort = h->d_abort; } }
     if (h->can_wpc) {
         for (int f = 0; f < 4; ++f) CKH(allow_max_smem(wpc_kernel_fn(M, f), maxsmem));
         {   /* f_int spill: one slot per (SM, channel warp); with WPC_CTAS > 1 two CTAs may share an SM -> fall back to per-channel slots */
@@ -338,7 +371,7 @@ extern "C" int b200fsk_create(b200fsk_t **out, const b200fsk_cfg_t *cfg, int nch
                 } else cudaGetLastError();
             }
         }
-        CKH(zalloc(&h->d_abort, 1));
+        if (!h->d_abort) CKH(zalloc(&h->d_abort, 1));
         kp.w_fint = h->d_fint; kp.w_abort = h->d_abort;
     }
 
@@ -463,7 +496,12 @@ static int launch(b200fsk *h, FskKParams &kp, cudaStream_t s, bool time_it)
     /* kernel choice: up to two channels per SM the per-channel pipeline wins (the oscillator recurrence bounds a channel);
        beyond that the per-sample instruction count decides and the many-channels-per-CTA kernel takes over */
     const bool wpc = h->can_wpc && (h->force_wpc || h->nchan > h->wpc_thresh);
-    if (wpc) {
+    const bool duo = !wpc && h->can_duo && (h->force_duo || (h->duo_auto && h->nchan > h->nsm && h->nchan <= 2 * h->nsm));
+    if (duo) {
+        void *args[] = {(void *)&kp};
+        CK(cudaLaunchKernel(duo_kernel_fn(kp.M, kp.fmt), dim3((h->nchan + DUO_G - 1) / DUO_G), dim3(DUO_THREADS), args, h->smem_duo, s));
+        h->last_kind = 3;
+    } else if (wpc) {
         /* channels per CTA: fill whole waves of one CTA per SM */
         int G = h->wpc_G;
         const int slots = h->nsm * WPC_CTAS, per_wave = G * slots, waves = (h->nchan + per_wave - 1) / per_wave;

@@ -232,7 +232,7 @@ class FskBatch:
     def last_kernel_ms(self) -> float:
         return float(self.L.b200fsk_last_kernel_ms(self.h))
 
-    KERNEL_NAMES = {-1: "none", 0: "fsk_demod_kernel", 1: "fsk_demod_pipe_kernel", 2: "fsk_wpc_kernel"}
+    KERNEL_NAMES = {-1: "none", 0: "fsk_demod_kernel", 1: "fsk_demod_pipe_kernel", 2: "fsk_wpc_kernel", 3: "fsk_duo_kernel"}
 
     def last_kernel(self) -> str:
         """name of the frame kernel the most recent launch used (include/b200fsk.h: b200fsk_last_kernel_kind)"""

@@ -43,7 +43,7 @@ def channels(seed, nchan, nsamp, kw):
     return iq
 
 
-@pytest.mark.parametrize("mode", ["auto", "serial", "wpc"])
+@pytest.mark.parametrize("mode", ["auto", "serial", "wpc", "duo"])
 @pytest.mark.parametrize("name", list(CONFIGS))
 def test_push_matches_oracle(cuda, name, mode):
     cfg, kw = CONFIGS[name]
@@ -70,7 +70,7 @@ def test_push_matches_oracle(cuda, name, mode):
         assert b.Sf(c).tobytes() == orc.Sf().tobytes()
 
 
-@pytest.mark.parametrize("mode", ["auto", "serial", "wpc"])
+@pytest.mark.parametrize("mode", ["auto", "serial", "wpc", "duo"])
 def test_chunked_push_equals_single_push(cuda, mode):
     """Streaming: arbitrary chunking of the input must not change a single output bit (carry logic)."""
     cfg = po.RS41
@@ -90,7 +90,7 @@ def test_chunked_push_equals_single_push(cuda, mode):
         assert np.concatenate(got[c]).tobytes() == ref[c].tobytes()
 
 
-@pytest.mark.parametrize("mode", ["auto", "wpc"])
+@pytest.mark.parametrize("mode", ["auto", "wpc", "duo"])
 def test_max_frames_cap_and_stats_cadence(cuda, mode):
     cfg = po.RS41
     iq = channels(11, 1, 60_000, {})
@@ -112,7 +112,7 @@ def test_max_frames_cap_and_stats_cadence(cuda, mode):
     assert np.concatenate(got).tobytes() == ref.tobytes()
 
 
-@pytest.mark.parametrize("mode", ["auto", "wpc"])
+@pytest.mark.parametrize("mode", ["auto", "wpc", "duo"])
 @pytest.mark.parametrize("fmt", ["f32", "cu8", "s16"])
 def test_input_formats(cuda, fmt, mode):
     cfg = po.FskConfig(48000, 4800, 2, 10, 50, lower=(0 if fmt == "s16" else None))
@@ -169,7 +169,7 @@ def test_reference_named_api(cuda):
     fsk.fsk_destroy(m)
 
 
-@pytest.mark.parametrize("mode", ["auto", "wpc"])
+@pytest.mark.parametrize("mode", ["auto", "wpc", "duo"])
 def test_nan_input_follows_reference_early_return(cuda, mode):
     """fsk.c:702-704: a NaN timing estimate returns early and the CLI re-emits its stale buffer."""
     cfg = po.FskConfig(48000, 4800, 2, 10, 50, softinv=True)
@@ -219,7 +219,7 @@ def test_mixed_2fsk_4fsk_batch(cuda):
     mb.close()
 
 
-@pytest.mark.parametrize("mode", ["auto", "wpc"])
+@pytest.mark.parametrize("mode", ["auto", "wpc", "duo"])
 def test_empty_and_sub_frame_pushes(cuda, mode):
     """Edge cases of the stream interface: zero-length pushes, pushes shorter than a frame (nothing may come out until a
     whole frame is available), and sample-by-sample feeding around a frame boundary."""
@@ -239,7 +239,7 @@ def test_empty_and_sub_frame_pushes(cuda, mode):
     assert np.concatenate(got).tobytes() == ref.tobytes() and len(recs) == 4
 
 
-@pytest.mark.parametrize("mode", ["pipe", "auto"])
+@pytest.mark.parametrize("mode", ["pipe", "auto", "duo"])
 def test_more_channels_than_resident_ctas(cuda, mode):
     """600 channels > 2 CTAs x 148 SMs: several waves of channel CTAs, every channel still bit-exact; ragged content
     (noise-only, different SNR / ppm / offsets) exercises different nin sequences per channel.  'auto' picks the
