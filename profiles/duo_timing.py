@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 os.environ["B200FSK_KERNEL"] = "duo"
 from radiosonde_auto_rx_b200 import fsk, siggen
-fsk.LIB_PATH = os.path.join(ROOT, "radiosonde_auto_rx_b200", "libb200fsk_prof.so")
+fsk.LIB_PATH = os.environ.get("B200FSK_LIB", os.path.join(ROOT, "radiosonde_auto_rx_b200", "libb200fsk_prof.so"))
 import torch
 nchan = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 nsamp = int(sys.argv[2]) if len(sys.argv) > 2 else 262144
@@ -33,3 +33,6 @@ print(f"nchan={nchan} kernel={b.last_kernel()} kernel_ms={b.last_kernel_ms():.3f
 for name, s in (("C0", 0), ("C1", 4), ("E0", 1), ("E1", 2), ("E2", 5), ("D ", 3)):
     print(f"  {name}: wait {m[2*s]:8.0f}  total {m[2*s+1]:8.0f}  busy {m[2*s+1]-m[2*s]:8.0f}")
 print(f"  OSC: stepping {m0[12]:8.0f} ({m0[12]/3000:.1f} cyc/step)  events {m0[13]:8.0f}  total {m0[14]:8.0f}")
+if os.environ.get("DUO_DETAIL"):
+    print(f"  C1 detail: mix {m[4]:8.0f}  integrate {m[5]:8.0f}  publish {m[10]:8.0f}")
+    print(f"  D  detail: terms {m[2]:8.0f}  accumulate {m[3]:8.0f}  time+dec {m[11]:8.0f}")

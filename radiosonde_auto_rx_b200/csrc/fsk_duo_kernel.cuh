@@ -25,19 +25,30 @@
 
 #ifdef FSK_PROFILE
 #define DW(expr) ([&]() { const long long t_ = clock64(); const bool r_ = (expr); dwait += clock64() - t_; return r_; }())
-#define DPROF_BEGIN long long dwait = 0; const long long drole0 = clock64();
+#define DPROF_BEGIN long long dwait = 0, dt0 = 0, dt1 = 0, dt2 = 0, dtm = 0; const long long drole0 = clock64(); (void)dt0; (void)dt1; (void)dt2; (void)dtm;
+#define DT_MARK dtm = clock64();
+#define DT_ADD(v) do { const long long n_ = clock64(); v += n_ - dtm; dtm = n_; } while (0)
+#define DPROF_RAW(q, v) do { if (lane == 0 && p.prof) p.prof[(long long)(blockIdx.x * DUO_G + (g < 0 ? 0 : g)) * 16 + (q)] += (v); } while (0)
 #define DPROF_END(slot) do { if (lane == 0 && p.prof) { p.prof[(long long)(blockIdx.x * DUO_G + (g < 0 ? 0 : g)) * 16 + 2 * (slot)] += dwait; p.prof[(long long)(blockIdx.x * DUO_G + (g < 0 ? 0 : g)) * 16 + 2 * (slot) + 1] += clock64() - drole0; } } while (0)
 #else
 #define DW(expr) (expr)
 #define DPROF_BEGIN
 #define DPROF_END(slot)
+#define DT_MARK
+#define DT_ADD(v)
+#define DPROF_RAW(q, v)
 #endif
 #define DUO_G       2
 #define DUO_THREADS 512          /* 16 warp slots; slot % 4 == 0 is sub-partition 0: slot 0 = OSC, slots 4, 8, 12 exit at once */
 #define DUO_RN      1024         /* ring slots per tone (f_dc; the oscillator writes its phases here first) */
 #define DUO_RS      (DUO_RN + 2)
 #define DUO_BLK     128
+#ifndef DUO_NE
 #define DUO_NE      3            /* EST warps per channel: E0 (leader: its rounds + the ordered Sf recursion + the estimate), E1, E2 (helpers) */
+#endif
+#ifndef DUO_CILP
+#define DUO_CILP 0               /* integrate two outputs per lane at a time */
+#endif
 #define DUO_MAGSETS (1 + 2 * (DUO_NE - 1))   /* |X| row sets of 4 windows: E0 uses set 0, every helper alternates between two of its own */
 
 struct DuoChan {                 /* per-channel hand-off words (static shared memory) */
@@ -79,10 +90,18 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) fsk_duo_kernel(const FskKParam
 
     /* ---------------------------------------------------------------- role table ---------------------------------------------------- */
     int g = -1, role = -1;                       /* role: 0 C0, 1 E0, 2 E1, 3 D, 4 C1, 5 E2; sub-partition = slot % 4 (0 is the oscillator's) */
-    switch (warp) {
-        case 1: g = 0; role = 0; break;  case 2: g = 0; role = 1; break;  case 3: g = 0; role = 2; break;  case 5: g = 0; role = 3; break;  case 6: g = 0; role = 4; break;  case 7: g = 0; role = 5; break;
-        case 9: g = 1; role = 0; break;  case 10: g = 1; role = 1; break; case 11: g = 1; role = 2; break; case 13: g = 1; role = 3; break; case 14: g = 1; role = 4; break; case 15: g = 1; role = 5; break;
-        default: break;
+#ifndef DUO_ROLEMAP
+#define DUO_ROLEMAP 0
+#endif
+    {
+        /* slot -> role: sub-partition 1 = slots 1,5,9,13; 2 = 2,6,10,14; 3 = 3,7,11,15 */
+#if DUO_ROLEMAP == 0
+        constexpr signed char R[16] = { -1, 0, 1, 2,  -1, 3, 4, 5,  -1, 0, 1, 2,  -1, 3, 4, 5 };   /* SMSP1: C0 D | SMSP2: E0 C1 | SMSP3: E1 E2 */
+#else
+        constexpr signed char R[16] = { -1, 0, 1, 2,  -1, 5, 4, 3,  -1, 0, 1, 2,  -1, 5, 4, 3 };   /* SMSP1: C0 E2 | SMSP2: E0 C1 | SMSP3: E1 D */
+#endif
+        role = R[warp];
+        if (role >= 0) g = warp >= 8 ? 1 : 0;
     }
 
     if (warp == 0) {
@@ -194,6 +213,7 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) fsk_duo_kernel(const FskKParam
     const int nrounds = (numffts + 3) / 4;
     const int tcap = p.d_tcap;
 
+    if (role == 5 && DUO_NE < 3) return;
     if (role == 1 || role == 2 || role == 5) {
         /* =========================== E0 / E1 / E2: estimator, one frame ahead ============================== */
         const int me = role == 1 ? 0 : (role == 2 ? 1 : 2);          /* 0: leader (its rounds + Sf recursion + estimate); 1, 2: helpers */
@@ -218,19 +238,19 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) fsk_duo_kernel(const FskKParam
             float *Sf_out = Sfbuf + (kk & 1) * Ndft;
             bool dead = false;
             for (int r = me; r < nrounds; r += DUO_NE) {
-                if (me > 0) {                                        /* helper: one round into one of its two row sets */
-                    const int n = mycnt;
-                    if (n >= 2 && !DW(wpc_wait_ge(&D.iir_h[me - 1], n - 1, &ctl, 100))) { dead = true; break; }   /* the set is free again */
-                    float *rows = magb + (1 + 2 * (me - 1) + (n & 1)) * 4 * F128_MSTRIDE;
-                    est_round128<FMT, true>(p, gbase + ck, 4 * r, numffts, F, s_tw, L128, nullptr, nullptr, lane, rows - 4 * r * F128_MSTRIDE);
-                    mycnt = n + 1;
-                    __syncwarp();
-                    if (lane == 0) st_rel(&D.eh_done[me - 1], n + 1);
+                /* one call site for the FFT body (instruction-cache footprint): helpers write one of their two row sets, the leader set 0 */
+                float *rows = magb;
+                if (me > 0) {
+                    if (mycnt >= 2 && !DW(wpc_wait_ge(&D.iir_h[me - 1], mycnt - 1, &ctl, 100))) { dead = true; break; }   /* the set is free again */
+                    rows = magb + (1 + 2 * (me - 1) + (mycnt & 1)) * 4 * F128_MSTRIDE;
+                }
+                est_round128c<FMT>(p, gbase + ck, 4 * r, numffts, F, s_tw, L128, lane, rows - 4 * r * F128_MSTRIDE);
+                if (me > 0) {
+                    ++mycnt;
+                    if (lane == 0) st_rel(&D.eh_done[me - 1], mycnt);
                     continue;
                 }
-                /* leader: its own round, then rounds r .. r+NE-1 in window order through the Sf recursion (fsk.c:484-500) */
-                float *rows = magb;
-                est_round128<FMT, true>(p, gbase + ck, 4 * r, numffts, F, s_tw, L128, nullptr, nullptr, lane, rows - 4 * r * F128_MSTRIDE);
+                /* leader: rounds r .. r+NE-1 in window order through the Sf recursion (fsk.c:484-500) */
                 const float *hrow[DUO_NE - 1];
 #pragma unroll
                 for (int e = 0; e < DUO_NE - 1; ++e) {
@@ -242,8 +262,8 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) fsk_duo_kernel(const FskKParam
                 }
                 if (dead) break;
                 const float *Sf_src = r ? Sf_out : Sf_in;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
+#pragma unroll 2
+                for (int q = 0; q < 4; ++q) {                        /* two bins in flight: enough for a latency-bound chain, half the code */
                     const int i = lane + 32 * q, src = (i + 64) & 127;
                     float s = Sf_src[i];
 #pragma unroll
@@ -270,7 +290,9 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) fsk_duo_kernel(const FskKParam
                 if (lane == 0) st_rel(&ctl.seqE[g], kk + 1);
             }
         }
+#ifndef DUO_PROF_DETAIL
         DPROF_END(me == 0 ? 1 : (me == 1 ? 2 : 5));
+#endif
         return;                                                      /* Sf is written back by D (it knows how many frames really existed) */
     }
 
@@ -302,6 +324,7 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) fsk_duo_kernel(const FskKParam
             for (int s0 = ck; s0 < fend; s0 += BLK) {
                 const int cnt = min(BLK, fend - s0);
                 if (!DW(wpc_wait_ge(&ctl.oscpos, s0 + cnt, &ctl, 100))) { dead = true; break; }
+                DT_MARK
                 float2 xv[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -319,6 +342,7 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) fsk_duo_kernel(const FskKParam
                     }
                 }
                 __syncwarp();
+                DT_ADD(dt0);
                 const int mixed_end = s0 + cnt;
                 int i_hi = 0;
                 if (mixed_end - base >= Ts) i_hi = min(nfi, (mixed_end - base - Ts) / step + 1);
@@ -364,6 +388,15 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) fsk_duo_kernel(const FskKParam
                         }
                     }
                 };
+#if !DUO_CILP
+                for (int e = lane; e < ni; e += 32) {
+                    const int ia = i_done + e;
+                    float2 a0v[MH];
+                    integ_one(ia, a0v);
+#pragma unroll
+                    for (int mm = 0; mm < MH; ++mm) fint[(size_t)(m0 + mm) * nfi + ia] = a0v[mm];
+                }
+#else
                 for (int e = lane; e < ni; e += 64) {                /* two outputs per lane in flight (independent add chains) */
                     const bool two = e + 32 < ni;
                     const int ia = i_done + e, ib = two ? ia + 32 : ia;
@@ -372,18 +405,24 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) fsk_duo_kernel(const FskKParam
 #pragma unroll
                     for (int mm = 0; mm < MH; ++mm) { fint[(size_t)(m0 + mm) * nfi + ia] = a0v[mm]; if (two) fint[(size_t)(m0 + mm) * nfi + ib] = a1v[mm]; }
                 }
+#endif
                 __syncwarp();
+                DT_ADD(dt1);
                 ++nblk_pub;
                 if (lane == 0) {
                     st_rel(&D.cons_blocks[tg], nblk_pub);
                     *(volatile int *)&D.free2[tg] = min(base + i_hi * step, fend - p.tailcap);
                 }
                 i_done = i_hi;
+                DT_ADD(dt2);
             }
             if (dead) break;
             c_end = fend;
         }
         DPROF_END(tg == 0 ? 0 : 4);
+#ifdef DUO_PROF_DETAIL
+        if (tg == 1) { DPROF_RAW(4, dt0); DPROF_RAW(5, dt1); DPROF_RAW(10, dt2); }
+#endif
         /* the integrator memory of the next launch: the ring rows of these tones are this warp's */
         for (int e = lane; e < MH * p.tailcap; e += 32) {
             const int m = m0 + e / p.tailcap, i = e % p.tailcap;
@@ -435,6 +474,7 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) fsk_duo_kernel(const FskKParam
             int i_hi = 0;
             if (mixed_end - base >= Ts) i_hi = min(nfi, (mixed_end - base - Ts) / step + 1);
             const int ni = i_hi - i_done;
+            DT_MARK
             for (int e = lane; e < ni; e += 64) {                    /* the timing terms of the outputs this block completed, two per lane in flight */
                 const int e1 = e + 32 < ni ? e + 32 : e;
                 const int ia = i_done + e, ib = i_done + e1;
@@ -446,6 +486,7 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) fsk_duo_kernel(const FskKParam
                 tre[e1] = __fmul_rn(fb, pb.x); tim[e1] = __fmul_rn(fb, pb.y);
             }
             __syncwarp();
+            DT_ADD(dt0);
             if (lane < 2) {
                 const float *t = lane ? tim : tre;
                 int j = 0;
@@ -457,11 +498,13 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) fsk_duo_kernel(const FskKParam
                 for (; j < ni; ++j) acc = __fadd_rn(acc, t[j]);
             }
             __syncwarp();
+            DT_ADD(dt1);
             ++blk_seen;
             i_done = i_hi;
         }
         }
         if (dead) break;
+        DT_MARK
         const float tr = __shfl_sync(0xffffffffu, acc, 0), ti = __shfl_sync(0xffffffffu, acc, 1);
         int nan = 0, nin_next = nin, low = 0, high = high_last; float fract = 0.0f;
         if (isnan(tr) || isnan(ti)) nan = 1;
@@ -559,8 +602,12 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) fsk_duo_kernel(const FskKParam
         __syncwarp();
         ++frames; ++k; ck = ck1; nin = nin_next; exists = exists_next;
         if (lane == 0) st_rel(&D.dec_frames, k);
+        DT_ADD(dt2);
     }
     DPROF_END(3);
+#ifdef DUO_PROF_DETAIL
+    DPROF_RAW(2, dt0); DPROF_RAW(3, dt1); DPROF_RAW(11, dt2);
+#endif
     if (dead && lane == 0 && p.w_abort) atomicExch(p.w_abort, 1);
     /* ---- this channel's state back to HBM ---- */
     {

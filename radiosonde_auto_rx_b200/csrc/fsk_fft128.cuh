@@ -137,3 +137,76 @@ __device__ __forceinline__ void est_round128(const FskKParams &p, long long gpos
     }
     __syncwarp();
 }
+
+/* Compact form of est_round128<FMT, true> for kernels whose warps run DIFFERENT roles on one SM (fsk_duo_kernel): there the 32 KB
+ * instruction cache level, not the issue slots, is the scarce resource (profiles/r02_notes.md: 28 % of the warp samples of the first
+ * version were "no instruction", hit rate 62 %), so the body is kept near 10 KB: pass 1 is a rolled loop over the two blocks of a lane
+ * with the next block's samples prefetched, and the square roots run as a rolled in-place pass over the rows.  Same butterflies,
+ * same operand order, same results. */
+template <int FMT>
+__device__ __forceinline__ void est_round128c(const FskKParams &p, long long gpos, int j0, int numffts, float2 *F, const float2 *s_tw,
+                                           const F128Lane &L, int lane, float *magout)
+{
+    const int B = lane & 15, qa = lane >> 4;
+    const float2 w0 = s_tw[0], w16 = s_tw[16], w32 = s_tw[32], w48 = s_tw[48];
+    float2 xn[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+        xn[t] = (j0 + qa < numffts) ? load_sample_t<FMT>(p.in, gpos + (long long)(j0 + qa) * 64 + L.idx0 + f128_off(t)) : make_float2(0.0f, 0.0f);
+#pragma unroll 1
+    for (int r = 0; r < 2; ++r) {
+        float2 x[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) x[t] = xn[t];
+        if (r == 0) {
+            const int j = j0 + qa + 2;
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+                xn[t] = (j < numffts) ? load_sample_t<FMT>(p.in, gpos + (long long)j * 64 + L.idx0 + f128_off(t)) : make_float2(0.0f, 0.0f);
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) x[t] = make_float2(__fmul_rn(L.h[t], x[t].x), __fmul_rn(L.h[t], x[t].y));   /* fsk.c:470-478 */
+        kf_bfly2_rn(x[0], x[1], w0); kf_bfly2_rn(x[2], x[3], w0);
+        kf_bfly2_rn(x[4], x[5], w0); kf_bfly2_rn(x[6], x[7], w0);
+        kf_bfly4_rn(x[0], x[2], x[4], x[6], w0, w0, w0);
+        kf_bfly4_rn(x[1], x[3], x[5], x[7], w16, w32, w48);
+        float2 *dst = F + (qa + 2 * r) * F128_STRIDE + 9 * B;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) dst[t] = x[t];
+    }
+    __syncwarp();
+    /* pass 2 in two rolled sub-passes over this lane's own 16 slots (same lane writes and reads: no warp sync in between) */
+    const int u = lane & 7, q = lane >> 3;
+    float2 *base = F + q * F128_STRIDE + u;
+    {
+        const float2 a1 = s_tw[4 * u], a2 = s_tw[8 * u], a3 = s_tw[12 * u];                    /* radix 4, m = 8 */
+#pragma unroll 2
+        for (int b = 0; b < 4; ++b) {
+            float2 *sl = base + 36 * b;
+            float2 y0 = sl[0], y1 = sl[9], y2 = sl[18], y3 = sl[27];
+            kf_bfly4_rn(y0, y1, y2, y3, a1, a2, a3);
+            sl[0] = y0; sl[9] = y1; sl[18] = y2; sl[27] = y3;
+        }
+    }
+    {
+        const bool live = j0 + q < numffts;
+        float *mag = magout + (j0 + q) * F128_MSTRIDE + u;
+#pragma unroll 2
+        for (int jj = 0; jj < 4; ++jj) {                             /* radix 4, m = 32, then |X|^2 */
+            const int v = u + 8 * jj;
+            const float2 *sl = base + 9 * jj;
+            float2 y0 = sl[0], y1 = sl[36], y2 = sl[72], y3 = sl[108];
+            kf_bfly4_rn(y0, y1, y2, y3, s_tw[v], s_tw[2 * v], s_tw[3 * v]);
+            if (live) { mag[8 * jj] = mag2_rn(y0); mag[8 * (jj + 4)] = mag2_rn(y1); mag[8 * (jj + 8)] = mag2_rn(y2); mag[8 * (jj + 12)] = mag2_rn(y3); }
+        }
+    }
+    __syncwarp();
+    const int nw = min(4, numffts - j0);
+#pragma unroll 1
+    for (int w = 0; w < nw; ++w) {                                   /* |X| = sqrt(|X|^2), in place, rolled */
+        float *row = magout + (j0 + w) * F128_MSTRIDE + lane;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) row[32 * k] = __fsqrt_rn(row[32 * k]);
+    }
+    __syncwarp();
+}

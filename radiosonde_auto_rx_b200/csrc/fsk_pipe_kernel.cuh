@@ -153,22 +153,31 @@ __device__ __forceinline__ float2 osc_pairs(float2 ph, const float2 d, float2 *d
 {
     int j = 0;
 #if !PIPE_GRING
-    if ((PIPE_OSC_PIPELINED || pipelined) && n >= 32) {
+    if (PIPE_OSC_PIPELINED || pipelined) {
+        /* 16 steps per iteration in two register sets: set A is stored pair by pair while set B is computed, set B in one burst at the
+         * end of the iteration -- its registers are rewritten 8 steps (~85 cycles) later, set A's 7+ steps after their stores.  No
+         * prologue/epilogue: with the control code around it the whole oscillator loop stays inside the 6 KB L0 instruction cache of its
+         * sub-partition (profiles/r02_notes.md: instruction fetch was 1/3 of the step time before). */
         float2 a[8], b[8];
-        a[0] = cmul_rn(ph, d);
+#pragma unroll 1
+        for (; j + 16 <= n; j += 16) {
+            a[0] = cmul_rn(ph, d);
 #pragma unroll
-        for (int s = 1; s < 8; ++s) a[s] = cmul_rn(a[s - 1], d);
-        for (; j + 32 <= n; j += 16) {                       /* invariant: a[] = steps j+1..j+8, not stored yet */
+            for (int s = 1; s < 8; ++s) a[s] = cmul_rn(a[s - 1], d);
             b[0] = cmul_rn(a[7], d);
 #pragma unroll
             for (int s = 1; s < 8; ++s) { b[s] = cmul_rn(b[s - 1], d); if (s & 1) sts128(dst + j + s - 1, a[s - 1], a[s]); }
-            a[0] = cmul_rn(b[7], d);
+            ph = b[7];
 #pragma unroll
-            for (int s = 1; s < 8; ++s) { a[s] = cmul_rn(a[s - 1], d); if (s & 1) sts128(dst + j + 8 + s - 1, b[s - 1], b[s]); }
+            for (int s = 1; s < 8; s += 2) sts128(dst + j + 8 + s - 1, b[s - 1], b[s]);
         }
-#pragma unroll
-        for (int s = 1; s < 8; s += 2) sts128(dst + j + s - 1, a[s - 1], a[s]);
-        ph = a[7]; j += 8;
+#pragma unroll 1
+        for (; j < n; j += 2) {
+            const float2 t = cmul_rn(ph, d);
+            ph = cmul_rn(t, d);
+            sts128(dst + j, t, ph);
+        }
+        return ph;
     }
 #endif
 #pragma unroll 4
