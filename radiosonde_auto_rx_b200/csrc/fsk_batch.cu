@@ -329,7 +329,7 @@ extern "C" int b200fsk_create(b200fsk_t **out, const b200fsk_cfg_t *cfg, int nch
         o2 = (o2 + 127) & ~(size_t)127; o2 += (M == 2) ? 32 : 64;          /* bank offset between the two channels' rings (oscillator stores) */
         kp.d_chan_stride = (int)o2;
         h->smem_duo = (size_t)kp.d_chan0 + (size_t)DUO_G * o2;
-        h->can_duo = (Ndft == 128) && (f0 == f1) && (f0 - 1 >= 1) && (3 * Ts + 2 * DUO_BLK + 16 <= DUO_RN) && (nfi >= 2) && (32 / M >= DUO_G) &&
+        h->can_duo = (Ndft == 128) && (f0 == f1) && (f0 - 1 >= 1) && (3 * Ts + 2 * DUO_BLK + 16 <= DUO_RN) && (N - Ts / 2 > 2 * DUO_BLK) && (nfi >= 2) && (32 / M >= DUO_G) &&
                      (h->smem_duo + 4096 <= (size_t)maxsmem);
         const char *force = getenv("B200FSK_KERNEL");
         h->force_duo = h->can_duo && force && !strcmp(force, "duo");

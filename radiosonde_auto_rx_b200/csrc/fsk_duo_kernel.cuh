@@ -46,6 +46,12 @@
 #ifndef DUO_NE
 #define DUO_NE      3            /* EST warps per channel: E0 (leader: its rounds + the ordered Sf recursion + the estimate), E1, E2 (helpers) */
 #endif
+#ifndef DUO_PREFETCH2
+#define DUO_PREFETCH2 1
+#endif
+#ifndef DUO_BACKOFF
+#define DUO_BACKOFF 1
+#endif
 #ifndef DUO_CILP
 #define DUO_CILP 0               /* integrate two outputs per lane at a time */
 #endif
@@ -91,7 +97,7 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) fsk_duo_kernel(const FskKParam
     /* ---------------------------------------------------------------- role table ---------------------------------------------------- */
     int g = -1, role = -1;                       /* role: 0 C0, 1 E0, 2 E1, 3 D, 4 C1, 5 E2; sub-partition = slot % 4 (0 is the oscillator's) */
 #ifndef DUO_ROLEMAP
-#define DUO_ROLEMAP 0
+#define DUO_ROLEMAP 1
 #endif
     {
         /* slot -> role: sub-partition 1 = slots 1,5,9,13; 2 = 2,6,10,14; 3 = 3,7,11,15 */
@@ -169,7 +175,7 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) fsk_duo_kernel(const FskKParam
 #ifdef FSK_PROFILE
             const long long ts_ = clock64();
 #endif
-            if (valid) {
+            if (act) {                                               /* only active chains: see fsk_wpc_kernel.cuh */
                 float2 *dst = myring + (pos & RMASK);
                 int j = 0;
                 if (pos & 1) { ph = cmul_rn(ph, d); dst[0] = ph; j = 1; }
@@ -212,6 +218,9 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) fsk_duo_kernel(const FskKParam
     const int numffts = (int)floorf(__fdiv_rn((float)nin_min, (float)(Ndft / 2))) - 1;
     const int nrounds = (numffts + 3) / 4;
     const int tcap = p.d_tcap;
+    const int sshift = (step & (step - 1)) == 0 ? 31 - __clz(step) : -1;     /* step is a power of two in every configuration the
+                                                                                 reference's CLIs produce: shift instead of a ~40-instruction division per block */
+#define DUO_DIVSTEP(x) (sshift >= 0 ? ((x) >> sshift) : (x) / step)
 
     if (role == 5 && DUO_NE < 3) return;
     if (role == 1 || role == 2 || role == 5) {
@@ -228,7 +237,7 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) fsk_duo_kernel(const FskKParam
         int kk = 0, ck = 0, mycnt = 0;                               /* helper: rounds it produced */
         for (;; ++kk) {
             if (kk > 0) {                                            /* c_kk = c_{kk-1} + nin_{kk-1}: known once frame kk-1 is published */
-                if (!DW(wpc_wait_ge(&ctl.seqT[g], kk, &ctl, 200))) break;
+                if (!DW(wpc_wait_ge_bo(&ctl.seqT[g], kk, &ctl, 200, 1600))) break;   /* a frame ahead: long wait, latency irrelevant */
                 const int ninp = ld_vol(&ctl.ninv[g][(kk - 1) & 1]);
                 if (ninp < 0) break;                                 /* frame kk-1 does not exist */
                 ck = ld_vol(&D.cstart[(kk - 1) & 3]) + ninp;
@@ -241,7 +250,7 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) fsk_duo_kernel(const FskKParam
                 /* one call site for the FFT body (instruction-cache footprint): helpers write one of their two row sets, the leader set 0 */
                 float *rows = magb;
                 if (me > 0) {
-                    if (mycnt >= 2 && !DW(wpc_wait_ge(&D.iir_h[me - 1], mycnt - 1, &ctl, 100))) { dead = true; break; }   /* the set is free again */
+                    if (mycnt >= 2 && !DW(wpc_wait_ge_bo(&D.iir_h[me - 1], mycnt - 1, &ctl, 100, 800))) { dead = true; break; }   /* the set is free again */
                     rows = magb + (1 + 2 * (me - 1) + (mycnt & 1)) * 4 * F128_MSTRIDE;
                 }
                 est_round128c<FMT>(p, gbase + ck, 4 * r, numffts, F, s_tw, L128, lane, rows - 4 * r * F128_MSTRIDE);
@@ -256,7 +265,7 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) fsk_duo_kernel(const FskKParam
                 for (int e = 0; e < DUO_NE - 1; ++e) {
                     hrow[e] = nullptr;
                     if (r + 1 + e < nrounds) {
-                        if (!DW(wpc_wait_ge(&D.eh_done[e], hcnt[e] + 1, &ctl, 100))) { dead = true; break; }
+                        if (!DW(wpc_wait_ge_bo(&D.eh_done[e], hcnt[e] + 1, &ctl, 100, 400))) { dead = true; break; }
                         hrow[e] = magb + (1 + 2 * e + (hcnt[e] & 1)) * 4 * F128_MSTRIDE;
                     }
                 }
@@ -308,8 +317,10 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) fsk_duo_kernel(const FskKParam
         __syncwarp();
         if (lane == 0) { if (tg == 0) st_rel(&ctl.nsrel[g], nsamp_rel < 0 ? 0 : nsamp_rel); st_rel(&D.ring_ready[tg], 1); }
         int k = 0, nblk_pub = 0, c_end = 0;
+        float2 xa[4], xb[4];                                         /* samples of the next block and of the one after it */
+        bool primed = false;
         for (;; ++k) {
-            if (!DW(wpc_wait_ge(&ctl.seqT[g], k + 1, &ctl, 200))) break;
+            if (!DW(wpc_wait_ge_bo(&ctl.seqT[g], k + 1, &ctl, 100, 400))) break;
             const int nin = ld_vol(&ctl.ninv[g][k & 1]);
             if (nin < 0) break;
             const int ck = ld_vol(&D.cstart[k & 3]);
@@ -318,19 +329,40 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) fsk_duo_kernel(const FskKParam
             float2 *fint = fintb + (size_t)(k & 1) * M * nfi;
             int i_done = 0;
             bool dead = false;
-            float2 xn[4];
+            if (!primed) {                                           /* the first two blocks of this launch */
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { const int t = u * 32 + lane; xn[u] = (ck + t < fend) ? load_sample_t<FMT>(p.in, gbase + ck + t) : make_float2(0.0f, 0.0f); }
+                for (int u = 0; u < 4; ++u) {
+                    const int t = u * 32 + lane;
+                    xa[u] = (ck + t < nsamp_rel) ? load_sample_t<FMT>(p.in, gbase + ck + t) : make_float2(0.0f, 0.0f);
+                    xb[u] = (ck + BLK + t < nsamp_rel) ? load_sample_t<FMT>(p.in, gbase + ck + BLK + t) : make_float2(0.0f, 0.0f);
+                }
+                primed = true;
+            }
             for (int s0 = ck; s0 < fend; s0 += BLK) {
                 const int cnt = min(BLK, fend - s0);
                 if (!DW(wpc_wait_ge(&ctl.oscpos, s0 + cnt, &ctl, 100))) { dead = true; break; }
                 DT_MARK
+                /* samples: two blocks in flight (one was not enough to cover an L2/HBM round trip: 12 % of this warp's samples waited
+                 * here).  Block starts continue across the frame boundary (the next frame starts at fend; it is at least two blocks long) */
+                const int n1 = (s0 + BLK < fend) ? s0 + BLK : fend;
+#if DUO_PREFETCH2
+                const int n2 = (n1 >= fend) ? n1 + BLK : ((n1 + BLK < fend) ? n1 + BLK : fend);
+#else
+                const int n2 = n1;                                   /* debugging aid: one block in flight (xa is reloaded below) */
+#endif
                 float2 xv[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    xv[u] = xn[u];
-                    const int t = BLK + u * 32 + lane;
-                    xn[u] = (s0 + t < fend) ? load_sample_t<FMT>(p.in, gbase + s0 + t) : make_float2(0.0f, 0.0f);
+#if DUO_PREFETCH2
+                    xv[u] = xa[u]; xa[u] = xb[u];
+#else
+                    xv[u] = xa[u];
+#endif
+                    const int t = n2 + u * 32 + lane;
+                    xb[u] = (t < nsamp_rel) ? load_sample_t<FMT>(p.in, gbase + t) : make_float2(0.0f, 0.0f);
+#if !DUO_PREFETCH2
+                    xa[u] = xb[u];
+#endif
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -345,7 +377,7 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) fsk_duo_kernel(const FskKParam
                 DT_ADD(dt0);
                 const int mixed_end = s0 + cnt;
                 int i_hi = 0;
-                if (mixed_end - base >= Ts) i_hi = min(nfi, (mixed_end - base - Ts) / step + 1);
+                if (mixed_end - base >= Ts) i_hi = min(nfi, DUO_DIVSTEP(mixed_end - base - Ts) + 1);
                 const int ni = i_hi - i_done;
                 const bool pair_path = (step == 2) && !(Ts & 1);
                 const int par = base & 1;
@@ -472,7 +504,7 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) fsk_duo_kernel(const FskKParam
             if (!DW(wpc_wait_ge(&D.cons_blocks[0], blk_seen + 1, &ctl, 100)) || !DW(wpc_wait_ge(&D.cons_blocks[1], blk_seen + 1, &ctl, 100))) { dead = true; break; }
             const int mixed_end = min(ck + (b + 1) * BLK, ck1);
             int i_hi = 0;
-            if (mixed_end - base >= Ts) i_hi = min(nfi, (mixed_end - base - Ts) / step + 1);
+            if (mixed_end - base >= Ts) i_hi = min(nfi, DUO_DIVSTEP(mixed_end - base - Ts) + 1);
             const int ni = i_hi - i_done;
             DT_MARK
             for (int e = lane; e < ni; e += 64) {                    /* the timing terms of the outputs this block completed, two per lane in flight */
@@ -490,7 +522,7 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) fsk_duo_kernel(const FskKParam
             if (lane < 2) {
                 const float *t = lane ? tim : tre;
                 int j = 0;
-#pragma unroll 4
+#pragma unroll 8
                 for (; j + 4 <= ni; j += 4) {
                     const float4 v = *reinterpret_cast<const float4 *>(t + j);
                     acc = __fadd_rn(acc, v.x); acc = __fadd_rn(acc, v.y); acc = __fadd_rn(acc, v.z); acc = __fadd_rn(acc, v.w);

@@ -137,6 +137,11 @@ __device__ __forceinline__ void sts128(float2 *dst, float2 a, float2 b)
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
 }
 
+__device__ __forceinline__ void sts128a(unsigned addr, float2 a, float2 b)      /* the same on a shared-window byte address */
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
+}
+
 /* n oscillator steps (n even, dst 16-byte aligned) written to consecutive ring slots; paired 16-byte stores.
  * The recurrence is one dependent FMUL->FADD chain per lane; what it must not do is wait for its own stores.  A shared store reads its
  * source registers only when the memory pipe dequeues it, and until then the next write to those registers stalls (write-after-read on
@@ -154,23 +159,31 @@ __device__ __forceinline__ float2 osc_pairs(float2 ph, const float2 d, float2 *d
     int j = 0;
 #if !PIPE_GRING
     if (PIPE_OSC_PIPELINED || pipelined) {
-        /* 16 steps per iteration in two register sets: set A is stored pair by pair while set B is computed, set B in one burst at the
-         * end of the iteration -- its registers are rewritten 8 steps (~85 cycles) later, set A's 7+ steps after their stores.  No
-         * prologue/epilogue: with the control code around it the whole oscillator loop stays inside the 6 KB L0 instruction cache of its
-         * sub-partition (profiles/r02_notes.md: instruction fetch was 1/3 of the step time before). */
-        float2 a[8], b[8];
+        /* 16 steps per iteration in 16 registers, every pair stored ONE pair after it was computed; the last two pairs of an iteration
+         * are stored at the start of the next one (after the loop for the last iteration).  What this arrangement buys:
+         *  - a stored register is rewritten >= 13 steps (~140 cycles) after its store was issued (no write-after-read wait on the data),
+         *  - no store in the last two steps of the iteration, so the pointer increment at the loop end does not wait for a store that
+         *    still holds the address register (that wait was 10 % of the step time in the ncu capture: profiles/r02_notes.md),
+         *  - no prologue/epilogue code: with the control code around it the oscillator loop stays inside the 6 KB L0 instruction
+         *    cache of its sub-partition. */
+        float2 v[16];
+        unsigned sa = (unsigned)__cvta_generic_to_shared(dst);       /* byte address of dst + j */
+        bool pend = false;
 #pragma unroll 1
         for (; j + 16 <= n; j += 16) {
-            a[0] = cmul_rn(ph, d);
+            v[0] = cmul_rn(ph, d); v[1] = cmul_rn(v[0], d);
+            if (pend) sts128a(sa - 32, v[12], v[13]);
+            v[2] = cmul_rn(v[1], d); v[3] = cmul_rn(v[2], d);
+            if (pend) sts128a(sa - 16, v[14], v[15]);
+            sts128a(sa, v[0], v[1]);
 #pragma unroll
-            for (int s = 1; s < 8; ++s) a[s] = cmul_rn(a[s - 1], d);
-            b[0] = cmul_rn(a[7], d);
-#pragma unroll
-            for (int s = 1; s < 8; ++s) { b[s] = cmul_rn(b[s - 1], d); if (s & 1) sts128(dst + j + s - 1, a[s - 1], a[s]); }
-            ph = b[7];
-#pragma unroll
-            for (int s = 1; s < 8; s += 2) sts128(dst + j + 8 + s - 1, b[s - 1], b[s]);
+            for (int q = 2; q < 8; ++q) {
+                v[2 * q] = cmul_rn(v[2 * q - 1], d); v[2 * q + 1] = cmul_rn(v[2 * q], d);
+                if (q < 7) sts128a(sa + 16 * (q - 1), v[2 * q - 2], v[2 * q - 1]);
+            }
+            ph = v[15]; pend = true; sa += 128;
         }
+        if (pend) { sts128a(sa - 32, v[12], v[13]); sts128a(sa - 16, v[14], v[15]); }
 #pragma unroll 1
         for (; j < n; j += 2) {
             const float2 t = cmul_rn(ph, d);

@@ -68,6 +68,26 @@ __device__ __forceinline__ bool wpc_wait_ge(const int *flag, int want, WpcCtl *c
     }
 }
 
+/* the same with exponential back-off (ns0, 2 ns0, ... up to nsmax) for waits that are known to be long and off the critical path:
+ * the ncu capture of the duo kernel counted more than half of all issued warp instructions inside fixed-interval poll loops */
+__device__ __forceinline__ bool wpc_wait_ge_bo(const int *flag, int want, WpcCtl *ctl, unsigned ns0, unsigned nsmax)
+{
+    if (ld_acq(flag) >= want) return true;
+    const long long t0 = clock64();
+    unsigned ns = ns0;
+    for (unsigned it = 1;; ++it) {
+        __nanosleep(ns);
+        if (ld_acq(flag) >= want) return true;
+#if !defined(DUO_BACKOFF) || DUO_BACKOFF
+        ns = min(ns * 2u, nsmax);
+#endif
+        if ((it & 7u) == 0) {
+            if (ld_vol(&ctl->abort)) return false;
+            if (clock64() - t0 > WPC_SPIN_LIMIT) { *(volatile int *)&ctl->abort = 1; return false; }
+        }
+    }
+}
+
 template <int M, int FMT>
 __global__ void __launch_bounds__((WPC_MAXG + 1) * 32, WPC_CTAS) fsk_wpc_kernel(const FskKParams p)
 {
@@ -151,7 +171,9 @@ __global__ void __launch_bounds__((WPC_MAXG + 1) * 32, WPC_CTAS) fsk_wpc_kernel(
                 n = min(n, fit);
             }
             spin_t0 = 0;
-            if (valid) {                                            /* n steps, fsk.c:646-647; paired 16-byte stores */
+            if (act) {                                              /* n steps, fsk.c:646-647; paired 16-byte stores.  Only ACTIVE chains: a channel
+                                                                       that has ended is not covered by the ring-space check any more, and its
+                                                                       warp may still be consuming the last blocks of its last frame */
                 float2 *dst = myring + (pos & RMASK);
                 int j = 0;
                 if (pos & 1) { ph = cmul_rn(ph, d); dst[0] = ph; j = 1; }

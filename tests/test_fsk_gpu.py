@@ -298,3 +298,22 @@ def test_nin_dependent_window_count_uses_the_serial_kernel(cuda):
 def test_configuration_too_large_for_shared_memory_is_an_error(cuda):
     with pytest.raises(fsk.B200Error, match="error -3"):
         fsk.FskBatch(96000, 2400, 4, 10, 600, nchan=1)
+
+
+@pytest.mark.parametrize("mode", ["wpc", "duo"])
+def test_channels_that_end_at_different_samples_share_an_oscillator_warp(cuda, mode):
+    """Regression: the oscillator warp steps all its chains in lockstep; the chain of a channel whose last frame has ended must stop
+    writing that channel's ring (it is no longer covered by the ring-space check while the channel's consumers may still be in the
+    last blocks of the last frame).  The race was timing dependent, so the push is repeated."""
+    cfg, kw = CONFIGS["rs41"]
+    nchan, nsamp = 5, 150_000
+    iq = channels(104, nchan, nsamp, kw)
+    ref_b = make_batch(cfg, nchan, mode="serial")
+    ref, ref_frames = ref_b.push(iq, "cs16", soft=True)
+    for rep in range(12):
+        b = make_batch(cfg, nchan, mode=mode)
+        out, frames = b.push(iq, "cs16", soft=True)
+        assert np.array_equal(frames, ref_frames)
+        for c in range(nchan):
+            n = frames[c] * b.Nbits
+            assert out[c, :n].tobytes() == ref[c, :n].tobytes(), f"repetition {rep} ch{c}"
