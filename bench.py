@@ -696,9 +696,10 @@ def run_ours(args):
                            "input": "float2 [channel][sample] resident in HBM, 2 GiB/GPU > L2 (no flush needed)",
                            "parallelism": f"channel-sharded x{world}, no data-path collective",
                            "sweep": sweep,
-                           "sweep_note": "Msamples/s vs channels per GPU, device-resident; <= 2 channels per SM run one warp-specialised CTA per channel "
-                                         "(fsk_demod_pipe_kernel, bound by the per-channel oscillator recurrence), larger batches 15 channels per CTA sharing one "
-                                         "lane-per-chain oscillator warp (fsk_wpc_kernel, bound by instruction issue)"},
+                           "sweep_note": "Msamples/s vs channels per GPU, device-resident; the library picks the frame kernel by channels per SM: <= 1 one "
+                                         "warp-specialised CTA per channel (fsk_demod_pipe_kernel), 1..4 two channels per CTA around one oscillator warp that "
+                                         "owns a sub-partition (fsk_duo_kernel, bound by the oscillator recurrence + role coupling), beyond that 15 channels "
+                                         "per CTA sharing one lane-per-chain oscillator warp (fsk_wpc_kernel, bound by instruction issue)"},
                 "clocks": clk,
                 "parity": parity,
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": float(nsamp) * nchan * 4,
@@ -710,8 +711,8 @@ def run_ours(args):
                              "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel_name, "kernel_ms": kern_ms,
                              "algorithmic_bytes_per_sample": BYTES_PER_SAMPLE_F32, "peak_source": peak_src,
                              "note": "not HBM-bound: ~125 un-fusable FP32 operations per sample (no FMA allowed: bit-exactness) put the issue ceiling near 0.3 Tsps; "
-                                     "at 256 channels the per-channel oscillator recurrence (one sample per >= 10.7 SM cycles) caps the batch at ~47 Gsps; "
-                                     "see DESIGN.md 4.1 and profiles/"},
+                                     "at 256 channels (2 per SM on 128 of 148 SMs) the per-channel oscillator recurrence (one sample per >= 10.7 SM cycles, "
+                                     "13.6 measured inside the kernel) caps the batch at ~47 Gsps; see DESIGN.md 4.1 and profiles/r02_notes.md"},
             }
             if sweep:
                 best = max(sweep, key=lambda d: d["value"])

@@ -305,7 +305,7 @@ extern "C" int b200fsk_create(b200fsk_t **out, const b200fsk_cfg_t *cfg, int nch
         if (G > WPC_MAXG) G = WPC_MAXG;
         kp.w_ring = ring; kp.w_blk = blk; kp.w_chan_stride = (int)stride;
         h->wpc_G = G;
-        h->wpc_thresh = 4 * h->nsm - 1;                           /* measured cross-over (profiles/r02_notes.md): from 4 channels per SM the throughput kernel wins */
+        h->wpc_thresh = 4 * h->nsm;                               /* measured cross-over (profiles/r02_notes.md): beyond 4 channels per SM the throughput kernel wins */
         if (const char *t = getenv("B200FSK_WPC_THRESH")) h->wpc_thresh = atoi(t);
         h->can_wpc = (f0 == f1) && (f0 - 1 >= 1) && (3 * Ts + 2 * blk + 16 <= ring) && (nfi >= 2) && (Ndft <= 256) && G >= 1;
         const char *force = getenv("B200FSK_KERNEL");
@@ -333,6 +333,9 @@ extern "C" int b200fsk_create(b200fsk_t **out, const b200fsk_cfg_t *cfg, int nch
                      (h->smem_duo + 4096 <= (size_t)maxsmem);
         const char *force = getenv("B200FSK_KERNEL");
         h->force_duo = h->can_duo && force && !strcmp(force, "duo");
+        h->duo_auto = true;                                       /* measured (profiles/r02_notes.md): wins for nsm < nchan <= 4 nsm (one or two full waves of
+                                                                     2 channels per SM); at most one channel per SM the one-CTA-per-channel pipeline is faster */
+        if (const char *t = getenv("B200FSK_DUO")) h->duo_auto = atoi(t) != 0;
         if (force && strcmp(force, "duo")) h->can_duo = false;
     }
     const bool serial_fits = h->smem + 256 <= (size_t)maxsmem;
@@ -493,10 +496,10 @@ static int flush_pending(b200fsk *h)
 static int launch(b200fsk *h, FskKParams &kp, cudaStream_t s, bool time_it)
 {
     if (time_it) CK(cudaEventRecord(h->ev0, s));
-    /* kernel choice: up to two channels per SM the per-channel pipeline wins (the oscillator recurrence bounds a channel);
-       beyond that the per-sample instruction count decides and the many-channels-per-CTA kernel takes over */
-    const bool wpc = h->can_wpc && (h->force_wpc || h->nchan > h->wpc_thresh);
-    const bool duo = !wpc && h->can_duo && (h->force_duo || (h->duo_auto && h->nchan > h->nsm && h->nchan <= 2 * h->nsm));
+    /* kernel choice by channels per SM (all measured, profiles/r02_notes.md): <= 1: one CTA per channel (pipe); 1..4: two channels per
+       CTA around one oscillator warp (duo); beyond: 15 channels per CTA (wpc), where the per-sample instruction count decides */
+    const bool wpc = h->can_wpc && !h->force_duo && (h->force_wpc || h->nchan > h->wpc_thresh);
+    const bool duo = !wpc && h->can_duo && (h->force_duo || (h->duo_auto && h->nchan > h->nsm && h->nchan <= 4 * h->nsm));
     if (duo) {
         void *args[] = {(void *)&kp};
         CK(cudaLaunchKernel(duo_kernel_fn(kp.M, kp.fmt), dim3((h->nchan + DUO_G - 1) / DUO_G), dim3(DUO_THREADS), args, h->smem_duo, s));

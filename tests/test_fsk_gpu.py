@@ -317,3 +317,29 @@ def test_channels_that_end_at_different_samples_share_an_oscillator_warp(cuda, m
         for c in range(nchan):
             n = frames[c] * b.Nbits
             assert out[c, :n].tobytes() == ref[c, :n].tobytes(), f"repetition {rep} ch{c}"
+
+
+def test_between_one_and_four_channels_per_sm_the_library_picks_the_duo_kernel(cuda):
+    """300 channels on 148 SMs = two waves of two-channel CTAs, the last CTA of the second wave half filled; ragged starts."""
+    import torch
+    cfg = po.RS41
+    nchan, nsamp = 2 * torch.cuda.get_device_properties(0).multi_processor_count + 5, 40_000
+    base = siggen.fsk_batch(777, 32, nsamp)
+    base[5] = siggen.noise_iq(11, nsamp)
+    iq = np.tile(base, ((nchan + 31) // 32, 1, 1))[:nchan].copy()
+    rng = np.random.default_rng(3)
+    off = rng.integers(0, 2500, nchan).astype(np.int32)
+    off[:2] = 0
+    b = make_batch(cfg, nchan)
+    x = torch.from_numpy(iq).cuda()
+    d_off = torch.from_numpy(off).cuda()
+    maxf = b.max_frames(nsamp)
+    d_out = torch.zeros((nchan, maxf * b.Nbits), dtype=torch.float32, device="cuda")
+    b.demod_device(x, "cs16", nsamp, d_out, soft=True, in_stride=nsamp, out_stride=maxf * b.Nbits, d_in_off=d_off)
+    frames, consumed = b.counts()
+    assert b.last_kernel() == "fsk_duo_kernel"
+    out = d_out.cpu().numpy()
+    for c in list(range(0, nchan, 23)) + [1, 5, 37, nchan - 2, nchan - 1]:
+        ref, cons, recs = po.Oracle(cfg).run_stream(iq[c, off[c]:])
+        assert frames[c] == len(recs) and consumed[c] == cons, c
+        assert out[c, : frames[c] * b.Nbits].tobytes() == ref.tobytes(), c
