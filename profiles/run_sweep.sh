@@ -1,2 +1,4 @@
-timeout 900 python profiles/sweep.py 20 duo:160 pipe:160 duo:180 pipe:180 duo:444 pipe:444 wpc:444 duo:592 wpc:592 duo:740 wpc:740 duo:888 wpc:888 duo:1036 wpc:1036 duo:1184 wpc:1184 wpc:2220 2>&1 | tail -18
-timeout 300 python profiles/sweep.py 16 wpc:2220 2>&1 | tail -1
+timeout 900 python -m pytest tests/test_fsk_gpu.py -q -m gpu 2>&1 | tail -30 > gpurun_out/test.log; tail -3 gpurun_out/test.log
+echo "== prof"; timeout 300 python profiles/duo_timing.py 256 262144 2>&1 | tail -8
+timeout 300 python profiles/sweep.py 20 duo:256 duo:296 2>&1 | tail -2
+timeout 800 ncu --set full --clock-control none --import-source on -k regex:fsk_duo -s 2 -c 1 -o gpurun_out/r02_duo python profiles/sweep.py 18 duo:256 2>&1 | tail -1

@@ -364,13 +364,22 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) fsk_duo_kernel(const FskKParam
                     xa[u] = xb[u];
 #endif
                 }
+                if (cnt == BLK) {                                    /* whole block (all but the last of a frame): no per-sample guards */
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int t = u * 32 + lane;
-                    if (t < cnt) {
-                        const int slot = (s0 + t) & RMASK;
+                    for (int u = 0; u < 4; ++u) {
+                        const int slot = (s0 + u * 32 + lane) & RMASK;
 #pragma unroll
-                        for (int mm = 0; mm < MH; ++mm) { const int m = m0 + mm; const float2 ph = ring[m * RS + slot]; ring[m * RS + slot] = cmul_rn(xv[u], make_float2(ph.x, -ph.y)); }
+                        for (int mm = 0; mm < MH; ++mm) { float2 *rp = ring + (m0 + mm) * RS + slot; const float2 ph = *rp; *rp = cmul_rn(xv[u], make_float2(ph.x, -ph.y)); }
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int t = u * 32 + lane;
+                        if (t < cnt) {
+                            const int slot = (s0 + t) & RMASK;
+#pragma unroll
+                            for (int mm = 0; mm < MH; ++mm) { const int m = m0 + mm; const float2 ph = ring[m * RS + slot]; ring[m * RS + slot] = cmul_rn(xv[u], make_float2(ph.x, -ph.y)); }
+                        }
                     }
                 }
                 __syncwarp();
@@ -421,6 +430,38 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) fsk_duo_kernel(const FskKParam
                     }
                 };
 #if !DUO_CILP
+                /* fast path (every block but the first and last of a frame): 64 outputs = two per lane, integrated side by side (two
+                 * independent add chains per tone), 16-byte loads at immediate offsets from one pointer per tone (no ring wrap inside) */
+                const int sl0 = (base + i_done * 2 - par) & RMASK;
+                if (pair_path && ni == 64 && sl0 + 2 * 63 + Ts + 2 <= RN) {
+                    const int ia = i_done + lane, h = Ts >> 1;
+                    float2 accA[MH], accB[MH];
+#pragma unroll
+                    for (int mm = 0; mm < MH; ++mm) {
+                        const float4 *q4 = reinterpret_cast<const float4 *>(ring + (m0 + mm) * RS + sl0 + 2 * lane);   /* output B: 64 slots = 32 float4 on */
+                        float2 a = make_float2(0.0f, 0.0f), b = make_float2(0.0f, 0.0f);
+                        if (!par) {
+#pragma unroll 5
+                            for (int q = 0; q < h; ++q) {
+                                const float4 va = q4[q], vb = q4[q + 32];
+                                a = cadd_rn(a, make_float2(va.x, va.y)); b = cadd_rn(b, make_float2(vb.x, vb.y));
+                                a = cadd_rn(a, make_float2(va.z, va.w)); b = cadd_rn(b, make_float2(vb.z, vb.w));
+                            }
+                        } else {
+                            { const float4 va = q4[0], vb = q4[32]; a = cadd_rn(a, make_float2(va.z, va.w)); b = cadd_rn(b, make_float2(vb.z, vb.w)); }
+#pragma unroll 4
+                            for (int q = 1; q < h; ++q) {
+                                const float4 va = q4[q], vb = q4[q + 32];
+                                a = cadd_rn(a, make_float2(va.x, va.y)); b = cadd_rn(b, make_float2(vb.x, vb.y));
+                                a = cadd_rn(a, make_float2(va.z, va.w)); b = cadd_rn(b, make_float2(vb.z, vb.w));
+                            }
+                            { const float4 va = q4[h], vb = q4[h + 32]; a = cadd_rn(a, make_float2(va.x, va.y)); b = cadd_rn(b, make_float2(vb.x, vb.y)); }
+                        }
+                        accA[mm] = a; accB[mm] = b;
+                    }
+#pragma unroll
+                    for (int mm = 0; mm < MH; ++mm) { fint[(size_t)(m0 + mm) * nfi + ia] = accA[mm]; fint[(size_t)(m0 + mm) * nfi + ia + 32] = accB[mm]; }
+                } else
                 for (int e = lane; e < ni; e += 32) {
                     const int ia = i_done + e;
                     float2 a0v[MH];
