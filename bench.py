@@ -696,10 +696,10 @@ def run_ours(args):
                            "input": "float2 [channel][sample] resident in HBM, 2 GiB/GPU > L2 (no flush needed)",
                            "parallelism": f"channel-sharded x{world}, no data-path collective",
                            "sweep": sweep,
-                           "sweep_note": "Msamples/s vs channels per GPU, device-resident; the library picks the frame kernel by channels per SM: <= 1 one "
-                                         "warp-specialised CTA per channel (fsk_demod_pipe_kernel), 1..4 two channels per CTA around one oscillator warp that "
-                                         "owns a sub-partition (fsk_duo_kernel, bound by the oscillator recurrence + role coupling), beyond that 15 channels "
-                                         "per CTA sharing one lane-per-chain oscillator warp (fsk_wpc_kernel, bound by instruction issue)"},
+                           "sweep_note": "Msamples/s vs channels per GPU, device-resident; the library picks the frame kernel by channels per SM: up to 4 the "
+                                         "duo kernel (one oscillator warp that owns a sub-partition + specialised warps per channel, two channels per CTA; "
+                                         "bound by the oscillator recurrence + role coupling), beyond that 15 channels per CTA sharing one lane-per-chain "
+                                         "oscillator warp (fsk_wpc_kernel, bound by instruction issue)"},
                 "clocks": clk,
                 "parity": parity,
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": float(nsamp) * nchan * 4,

@@ -496,13 +496,17 @@ static int flush_pending(b200fsk *h)
 static int launch(b200fsk *h, FskKParams &kp, cudaStream_t s, bool time_it)
 {
     if (time_it) CK(cudaEventRecord(h->ev0, s));
-    /* kernel choice by channels per SM (all measured, profiles/r02_notes.md): <= 1: one CTA per channel (pipe); 1..4: two channels per
-       CTA around one oscillator warp (duo); beyond: 15 channels per CTA (wpc), where the per-sample instruction count decides */
+    /* kernel choice by channels per SM (all measured, profiles/r02_notes.md): up to 4: the duo kernel (one oscillator warp on its own
+       sub-partition + specialised warps per channel; one channel per CTA while the batch has at most one channel per SM, two otherwise);
+       beyond: 15 channels per CTA (wpc), where the per-sample instruction count decides.  The one-CTA-per-channel pipeline (pipe) and the
+       serial kernel serve the modem configurations the duo kernel is not eligible for (N_dft != 128, nin-dependent window count). */
     const bool wpc = h->can_wpc && !h->force_duo && (h->force_wpc || h->nchan > h->wpc_thresh);
-    const bool duo = !wpc && h->can_duo && (h->force_duo || (h->duo_auto && h->nchan > h->nsm && h->nchan <= 4 * h->nsm));
+    const bool duo = !wpc && h->can_duo && (h->force_duo || (h->duo_auto && h->nchan <= 4 * h->nsm));
     if (duo) {
         void *args[] = {(void *)&kp};
-        CK(cudaLaunchKernel(duo_kernel_fn(kp.M, kp.fmt), dim3((h->nchan + DUO_G - 1) / DUO_G), dim3(DUO_THREADS), args, h->smem_duo, s));
+        kp.d_G = (!h->force_duo && h->nchan <= h->nsm) ? 1 : DUO_G;   /* at most one channel per SM: spread them, one channel per CTA (19.9 vs 19.0 Gsps at 148) */
+        if (const char *t = getenv("B200FSK_DUO_G")) { const int v = atoi(t); if (v >= 1 && v <= DUO_G) kp.d_G = v; }   /* experiments: 1 = one channel per CTA */
+        CK(cudaLaunchKernel(duo_kernel_fn(kp.M, kp.fmt), dim3((h->nchan + kp.d_G - 1) / kp.d_G), dim3(DUO_THREADS), args, h->smem_duo, s));
         h->last_kind = 3;
     } else if (wpc) {
         /* channels per CTA: fill whole waves of one CTA per SM */

@@ -28,8 +28,8 @@
 #define DPROF_BEGIN long long dwait = 0, dt0 = 0, dt1 = 0, dt2 = 0, dtm = 0; const long long drole0 = clock64(); (void)dt0; (void)dt1; (void)dt2; (void)dtm;
 #define DT_MARK dtm = clock64();
 #define DT_ADD(v) do { const long long n_ = clock64(); v += n_ - dtm; dtm = n_; } while (0)
-#define DPROF_RAW(q, v) do { if (lane == 0 && p.prof) p.prof[(long long)(blockIdx.x * DUO_G + (g < 0 ? 0 : g)) * 16 + (q)] += (v); } while (0)
-#define DPROF_END(slot) do { if (lane == 0 && p.prof) { p.prof[(long long)(blockIdx.x * DUO_G + (g < 0 ? 0 : g)) * 16 + 2 * (slot)] += dwait; p.prof[(long long)(blockIdx.x * DUO_G + (g < 0 ? 0 : g)) * 16 + 2 * (slot) + 1] += clock64() - drole0; } } while (0)
+#define DPROF_RAW(q, v) do { if (lane == 0 && p.prof) p.prof[(long long)(blockIdx.x * p.d_G + (g < 0 ? 0 : g)) * 16 + (q)] += (v); } while (0)
+#define DPROF_END(slot) do { if (lane == 0 && p.prof) { p.prof[(long long)(blockIdx.x * p.d_G + (g < 0 ? 0 : g)) * 16 + 2 * (slot)] += dwait; p.prof[(long long)(blockIdx.x * p.d_G + (g < 0 ? 0 : g)) * 16 + 2 * (slot) + 1] += clock64() - drole0; } } while (0)
 #else
 #define DW(expr) (expr)
 #define DPROF_BEGIN
@@ -113,8 +113,8 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) fsk_duo_kernel(const FskKParam
     if (warp == 0) {
         /* =========================== OSC (same protocol as fsk_wpc_kernel) ============================== */
         const int og = lane >> lgM, m = lane & (M - 1);
-        const int c = blockIdx.x * DUO_G + og;
-        const bool valid = og < DUO_G && c < p.nchan;
+        const int c = blockIdx.x * p.d_G + og;
+        const bool valid = og < p.d_G && c < p.nchan;
         if (valid) { wpc_wait_ge(&ctl.nsrel[og], 0, &ctl, 100); wpc_wait_ge(&dc[og].ring_ready[0], 1, &ctl, 100); wpc_wait_ge(&dc[og].ring_ready[1], 1, &ctl, 100); }
         const int nsrel = valid ? ld_vol(&ctl.nsrel[og]) : 0;
         float2 *myring = (float2 *)(smem + p.d_chan0 + (size_t)(valid ? og : 0) * p.d_chan_stride + p.d_ring_off) + (size_t)m * RS;
@@ -192,13 +192,13 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) fsk_duo_kernel(const FskKParam
             if (lane == 0) st_rel(&ctl.oscpos, pos);
         }
 #ifdef FSK_PROFILE
-        if (lane == 0 && p.prof) { long long *q = p.prof + (long long)(blockIdx.x * DUO_G) * 16; q[12] += o_step; q[13] += o_ev; q[14] += clock64() - o_t0; q[15] += pos; }
+        if (lane == 0 && p.prof) { long long *q = p.prof + (long long)(blockIdx.x * p.d_G) * 16; q[12] += o_step; q[13] += o_ev; q[14] += clock64() - o_t0; q[15] += pos; }
 #endif
         return;
     }
     if (g < 0) return;
-    const int c = blockIdx.x * DUO_G + g;
-    if (c >= p.nchan) return;
+    const int c = blockIdx.x * p.d_G + g;
+    if (g >= p.d_G || c >= p.nchan) return;                         /* d_G = 1: one channel per CTA (at most one channel per SM in the batch) */
 
     /* ---------------------------------------------------------------- per-channel memory ----------------------------------------------- */
     unsigned char *cb = smem + p.d_chan0 + (size_t)g * p.d_chan_stride;

@@ -77,6 +77,7 @@ struct FskKParams {
     int w_hann, w_tw, w_perm, w_mask, w_chan0, w_chan_stride, w_ring_off, w_fft_off, w_Sf_off, w_scr_off;
     /* two-channels-per-CTA kernel (fsk_duo_kernel.cuh): shared-memory byte offsets */
     int d_hann, d_tw, d_mask, d_chan0, d_chan_stride, d_ring_off, d_fint_off, d_fft_off, d_mag_off, d_Sf_off, d_scr_off, d_term_off, d_smax_off, d_tcap, d_phift;
+    int   d_G;                      /* duo kernel: channels per CTA in this launch (1 or 2) */
     float2 *w_fint; int *w_abort; int w_fint_slots, w_tcap, w_fp;
 };
 

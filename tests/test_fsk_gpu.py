@@ -43,7 +43,7 @@ def channels(seed, nchan, nsamp, kw):
     return iq
 
 
-@pytest.mark.parametrize("mode", ["auto", "serial", "wpc", "duo"])
+@pytest.mark.parametrize("mode", ["auto", "serial", "pipe", "wpc", "duo"])
 @pytest.mark.parametrize("name", list(CONFIGS))
 def test_push_matches_oracle(cuda, name, mode):
     cfg, kw = CONFIGS[name]
@@ -70,7 +70,7 @@ def test_push_matches_oracle(cuda, name, mode):
         assert b.Sf(c).tobytes() == orc.Sf().tobytes()
 
 
-@pytest.mark.parametrize("mode", ["auto", "serial", "wpc", "duo"])
+@pytest.mark.parametrize("mode", ["auto", "serial", "pipe", "wpc", "duo"])
 def test_chunked_push_equals_single_push(cuda, mode):
     """Streaming: arbitrary chunking of the input must not change a single output bit (carry logic)."""
     cfg = po.RS41
