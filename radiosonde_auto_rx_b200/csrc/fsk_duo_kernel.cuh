@@ -97,14 +97,16 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) fsk_duo_kernel(const FskKParam
     /* ---------------------------------------------------------------- role table ---------------------------------------------------- */
     int g = -1, role = -1;                       /* role: 0 C0, 1 E0, 2 E1, 3 D, 4 C1, 5 E2; sub-partition = slot % 4 (0 is the oscillator's) */
 #ifndef DUO_ROLEMAP
-#define DUO_ROLEMAP 1
+#define DUO_ROLEMAP 2
 #endif
     {
         /* slot -> role: sub-partition 1 = slots 1,5,9,13; 2 = 2,6,10,14; 3 = 3,7,11,15 */
 #if DUO_ROLEMAP == 0
         constexpr signed char R[16] = { -1, 0, 1, 2,  -1, 3, 4, 5,  -1, 0, 1, 2,  -1, 3, 4, 5 };   /* SMSP1: C0 D | SMSP2: E0 C1 | SMSP3: E1 E2 */
-#else
+#elif DUO_ROLEMAP == 1
         constexpr signed char R[16] = { -1, 0, 1, 2,  -1, 5, 4, 3,  -1, 0, 1, 2,  -1, 5, 4, 3 };   /* SMSP1: C0 E2 | SMSP2: E0 C1 | SMSP3: E1 D */
+#else
+        constexpr signed char R[16] = { -1, 0, 3, 1,  -1, 4, 5, 2,  -1, 0, 3, 1,  -1, 4, 5, 2 };   /* SMSP1: C0 C1 | SMSP2: D E2 | SMSP3: E0 E1 (same code per sub-partition) */
 #endif
         role = R[warp];
         if (role >= 0) g = warp >= 8 ? 1 : 0;
