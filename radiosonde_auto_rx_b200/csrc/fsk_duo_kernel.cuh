@@ -1,24 +1,34 @@
-/* fsk_duo_kernel.cuh -- two channels per CTA, one CTA per SM: the 149..296-channel form of the batched fsk_demod kernel (sm_100a).
+/* fsk_duo_kernel.cuh -- one CTA per SM that owns one or two channels: the batched fsk_demod kernel for up to 4 channels per SM (sm_100a).
  *
  * Why.  With two one-channel CTAs of fsk_demod_pipe_kernel on an SM the oscillator recurrence (utils/fsk.c:646-647) runs at 20.8 cycles/step
  * against 15-17 with one CTA and 10.65 alone (profiles/r02_notes.md): two oscillator warps at 2 of 32 lanes, twenty latency-bound role
- * warps behind named barriers, an instruction footprint that no longer stays cached (the oscillator loop's top stall becomes `no_instruction`).
- * fsk_wpc_kernel showed that ONE sequential warp with enough registers does a channel's whole consumer side at ~0.22 IPC.  This kernel
- * combines the two: per channel four sequential warps with flag hand-offs (no groups, no named barriers), one oscillator warp for both
- * channels that owns its SM sub-partition.
+ * warps behind named barriers, an instruction footprint that no longer stays cached.  fsk_wpc_kernel showed that ONE sequential warp with
+ * enough registers does a channel's whole consumer side at ~0.22 IPC.  This kernel combines the two: per channel a handful of sequential
+ * warps with flag hand-offs (no groups, no named barriers), one oscillator warp for both channels that owns its SM sub-partition.
  *
- *   slot 0       OSC   lane = channel*M + tone (fsk_wpc_kernel's oscillator verbatim); slots 4 and 8 exit at once: sub-partition 0 stays quiet
- *   per channel  E0    even EST rounds (4 windows each, fsk_fft128.cuh), the ordered Sf recursion over each pair of rounds, the tone
- *                      estimate -> dphi for the oscillator                                                           fsk.c:438-590
- *                E1    odd EST rounds -> |X| rows for E0
+ *   slot 0       OSC   lane = channel*M + tone (fsk_wpc_kernel's protocol; only ACTIVE chains store); slots 4, 8, 12 exit at once:
+ *                      sub-partition 0 stays quiet                                                                   fsk.c:644-651
+ *   per channel  E0    EST rounds r = 0 mod 3 (4 windows each, est_round128c), the ordered Sf recursion over its own and the helpers'
+ *                      |X| rows, the tone estimate -> dphi for the oscillator; runs one frame ahead                   fsk.c:438-590
+ *                E1,E2 EST rounds r = 1, 2 mod 3 -> |X| rows for E0 (two row sets each, eh_done / iir_h flags)
  *                C0,C1 one warp per half of the tones: blocks of 128 samples behind the oscillator: x*conj(phi) in place,
- *                      integrate-and-dump into the frame's f_int (shared memory, double-buffered)                    fsk.c:648,659-668
- *                      (one warp for both tones was the slowest role of the first version: 63k busy cycles per frame)
+ *                      integrate-and-dump into the frame's f_int (shared memory, double-buffered); samples two blocks ahead in
+ *                      registers; on whole blocks two outputs per lane side by side                                   fsk.c:648,659-668
  *                D     timing terms from f_int, their sequential accumulation, atan2f, ppm, next nin -> publishes frame k+1;
- *                      decisions, outputs, EbNo sums, frame record                                                   fsk.c:686-817
+ *                      decisions, outputs, EbNo sums, frame record, state write-back                                  fsk.c:686-817
+ *   role map (DUO_ROLEMAP 2): warps that run the same code share a sub-partition and its 6 KB L0 instruction cache:
+ *                      1: C0 C1 of both channels | 2: D E2 | 3: E0 E1.
  *
- * Eligibility: Ndft = 128 (the fused FFT), the pipeline's window-count condition, shared memory.  Arithmetic and order are those of the other
- * kernels; the same bit-exact tests run with B200FSK_KERNEL=duo.
+ * The design constraint that shaped the code: the instruction cache.  14 warps in 6 roles share 32 KB behind the L0s; the first version
+ * executed ~70 KB of hot code and spent 28 % of its warp samples without an instruction (profiles/r02_notes.md section 7).  Hence one call
+ * site for the FFT body, rolled loops wherever a role is latency-bound anyway, an oscillator loop without prologue/epilogue
+ * (profiles/code_size.py prints the static size per source region).
+ *
+ * p.d_G = channels per CTA of this launch: 2, or 1 while the batch has at most one channel per SM (then the second channel's warps exit).
+ * Eligibility (fsk_batch.cu): Ndft = 128 (the fused FFT), the pipeline's window-count condition, a frame of at least two blocks, shared
+ * memory.  Arithmetic and order are those of the other kernels; the same bit-exact tests run with B200FSK_KERNEL=duo and by default.
+ * Compile-time switches kept for experiments (profiles/r02_notes.md): DUO_NE (estimator warps, 2 or 3), DUO_ROLEMAP (0..2),
+ * DUO_PREFETCH2, DUO_BACKOFF, DUO_CILP; FSK_PROFILE adds per-role cycle counters (profiles/duo_timing.py).
  */
 #pragma once
 #include "fsk_wpc_kernel.cuh"
