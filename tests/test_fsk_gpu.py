@@ -1,4 +1,5 @@
 """GPU parity tests proper: the CUDA path through the C-ABI vs the oracle, bit for bit."""
+import os
 import numpy as np
 import pytest
 
@@ -343,3 +344,24 @@ def test_between_one_and_four_channels_per_sm_the_library_picks_the_duo_kernel(c
         ref, cons, recs = po.Oracle(cfg).run_stream(iq[c, off[c]:])
         assert frames[c] == len(recs) and consumed[c] == cons, c
         assert out[c, : frames[c] * b.Nbits].tobytes() == ref.tobytes(), c
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_every_production_line_against_the_unmodified_reference_library(cuda, name):
+    """The same comparison as test_push_matches_oracle, but straight against oracle/_ref/libfsk_ref.so (utils/fsk.c + kiss_fft compiled
+    unmodified with the reference's flags) instead of the C restatement: output bits, consumed samples and the carried spectrum Sf."""
+    if not os.path.exists(os.path.join(po.REF_DIR, "libfsk_ref.so")):
+        pytest.skip("oracle/_ref/libfsk_ref.so absent")
+    cfg, kw = CONFIGS[name]
+    nchan, nsamp = 3, 60_000
+    iq = channels(300 + len(name), nchan, nsamp, kw)
+    b = make_batch(cfg, nchan)
+    b.enable_stats(True)
+    out, frames = b.push(iq, "cs16", soft=cfg.soft, softinv=cfg.softinv)
+    for c in range(nchan):
+        ref, cons, recs, Sf = po.ref_run_stream(cfg, iq[c])
+        assert frames[c] == len(recs) > 0
+        assert out[c, : frames[c] * b.Nbits].tobytes() == ref.tobytes(), f"{name} ch{c}"
+        assert b.stats(c).samples == cons
+        mine = b.Sf(c)
+        assert mine.tobytes() == Sf[: mine.size].tobytes()
