@@ -177,9 +177,13 @@ int  b200fsk_get_eye_raw(b200fsk_t *h, int c, float *eye);
 long b200fsk_launch_count(const b200fsk_t *h);
 /* device time (ms) of the most recent demod kernel measured with CUDA events on its own stream; <0 if none */
 float b200fsk_last_kernel_ms(b200fsk_t *h);
-/* which frame kernel the handle's most recent launch used: 0 = fsk_demod_kernel (one stage at a time), 1 = fsk_demod_pipe_kernel
- * (one warp-specialised CTA per channel: <= 2 channels per SM), 2 = fsk_wpc_kernel (up to 15 channels per CTA sharing one
- * lane-per-chain oscillator warp: large batches), 3 = fsk_duo_kernel (two channels per CTA, one CTA per SM); -1 before the first launch.  All three produce identical bits. */
+/* which frame kernel the handle's most recent launch used: 3 = fsk_duo_kernel (one CTA per SM owning one or two channels: the default up to
+ * 4 channels per SM), 2 = fsk_wpc_kernel (up to 15 channels per CTA sharing one lane-per-chain oscillator warp: larger batches),
+ * 1 = fsk_demod_pipe_kernel (one warp-specialised CTA per channel) and 0 = fsk_demod_kernel (one stage at a time): the modem configurations the
+ * first two are not eligible for; -1 before the first launch.  All four produce identical bits.
+ * Environment (experiments and tests only): B200FSK_KERNEL=serial|pipe|duo|wpc forces a kernel for handles created afterwards,
+ * B200FSK_DUO=0 disables the duo kernel's automatic selection, B200FSK_DUO_G=1|2 its channels per CTA, B200FSK_WPC_THRESH=<n> moves the
+ * duo/wpc cross-over, B200FSK_L2PERSIST=0 drops the persisting L2 window of the wpc kernel. */
 int b200fsk_last_kernel_kind(const b200fsk_t *h);
 
 #ifdef __cplusplus
