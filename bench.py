@@ -453,31 +453,15 @@ def run_scatter(args):
     b = fsk.FskBatch(FS, RS, M, P, NSYM, 1000, MASK, LO, HI, 1, nchan=C, device=local)
     maxf = b.max_frames(B)
     d_out = torch.zeros((C, maxf * b.Nbits), dtype=torch.float32, device=dev)
-    recv = [torch.empty((C, B, 2), dtype=torch.int16, device=dev) for _ in range(2)]
-    copy_s, comp_s = torch.cuda.Stream(), torch.cuda.Stream()
-    ev_rx = [torch.cuda.Event() for _ in range(2)]
-    ev_done = [torch.cuda.Event() for _ in range(2)]
+    from radiosonde_auto_rx_b200 import shard
+    bs = shard.BlockScatter(C, B, dev, src=0)       # two receive buffers, copy stream + compute stream (radiosonde_auto_rx_b200/shard.py)
+    comp_s = bs.comp_stream
 
-    def post_scatter(t):
-        """block t -> recv[t % 2] on the copy stream (after the kernel that last read that buffer)"""
-        with torch.cuda.stream(copy_s):
-            copy_s.wait_event(ev_done[t % 2])
-            if world > 1:
-                # NCCL has no 16-bit integer type: one cs16 sample (I,Q) travels as one int32
-                lst = [cap[r * C:(r + 1) * C, t * B:(t + 1) * B].contiguous().view(torch.int32) for r in range(world)] if rank == 0 else None
-                dist.scatter(recv[t % 2].view(torch.int32), lst, src=0)
-            else:
-                recv[t % 2].copy_(cap[:, t * B:(t + 1) * B])
-            ev_rx[t % 2].record(copy_s)
+    def consume(buf, t, stream):
+        b.demod_device(buf, "cs16", B, d_out, soft=True, in_stride=B, out_stride=maxf * b.Nbits, stream=stream)
 
     def one_step():
-        post_scatter(0)
-        for t in range(T):
-            if t + 1 < T:
-                post_scatter(t + 1)
-            comp_s.wait_event(ev_rx[t % 2])
-            b.demod_device(recv[t % 2], "cs16", B, d_out, soft=True, in_stride=B, out_stride=maxf * b.Nbits, stream=comp_s)
-            ev_done[t % 2].record(comp_s)
+        bs.step(cap, T, consume)
 
     def barrier():
         if world > 1:

@@ -102,3 +102,49 @@ def test_broadcast_capture_shard_candidates_world2(built):
     assert chk == int(np.abs(wide.astype(np.int64)).sum())
     exp = [po.dft_oracle_run_wideband(wide, sr, f / sr, 15.0, True, False)[0] for f in (200e3, -300e3, 50e3)]
     assert codes == exp and exp[0] == 3 and exp[1] == 8 and exp[2] == 0
+
+
+def _bs_worker(rank, world, port, C, B, T, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    full = np.random.default_rng(99).integers(-32768, 32767, (world * C, T * B, 2), dtype=np.int16)   # every rank can rebuild the expectation
+    cap = torch.from_numpy(full) if rank == 0 else None
+    bs = shard.BlockScatter(C, B, "cpu", src=0)
+    ok = True
+    for step in range(2):                                   # the two receive buffers are reused across steps
+        got, order = [], []
+        bs.step(cap, T, lambda buf, t, stream: (got.append(buf.clone().numpy()), order.append(t), stream is None))
+        ok = ok and order == list(range(T))
+        ok = ok and np.array_equal(np.concatenate(got, axis=1), full[rank * C:(rank + 1) * C])
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_block_scatter_pipeline_world2():
+    """The streaming scatter bench.py --scatter times on GPUs (block t+1 in flight while block t is consumed), on the gloo backend:
+    every rank must see its channel block of every time block, in order, through the two alternating buffers."""
+    import torch.multiprocessing as mp
+    world, C, B, T = 2, 3, 500, 5
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_bs_worker, args=(r, world, port, C, B, T, q)) for r in range(world)]
+    [p.start() for p in ps]
+    res = dict(q.get(timeout=120) for _ in range(world))
+    [p.join(60) for p in ps]
+    assert all(p.exitcode == 0 for p in ps)
+    assert res == {0: True, 1: True}
+
+
+def test_block_scatter_single_rank_is_a_copy():
+    import torch
+    C, B, T = 2, 64, 3
+    full = np.random.default_rng(5).integers(-100, 100, (C, T * B, 2), dtype=np.int16)
+    bs = shard.BlockScatter(C, B, "cpu")
+    got = []
+    bs.step(torch.from_numpy(full), T, lambda buf, t, stream: got.append(buf.clone().numpy()))
+    assert np.array_equal(np.concatenate(got, axis=1), full)
